@@ -1,0 +1,313 @@
+// extern "C" boundary (include/dsm_b200.h): argument checks, exception -> status translation.
+#include <cstring>
+
+#include "lm.cuh"
+#include "mimi.cuh"
+
+using namespace dsm;
+
+struct dsm_mimi { MimiImpl* impl; };
+struct dsm_lm { LmImpl* impl; };
+struct dsm_asr { AsrImpl* impl; dsm_mimi* mimi; dsm_lm* lm; };
+
+template <typename F>
+static dsm_status guarded(F&& f) {
+  try {
+    f();
+    return DSM_OK;
+  } catch (const Error& e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    set_last_error("host allocation failed");
+    return DSM_ERR_OOM;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return DSM_ERR_INVALID_ARG;
+  } catch (...) {
+    set_last_error("unknown error");
+    return DSM_ERR_INVALID_ARG;
+  }
+}
+
+#define REQUIRE(cond, msg) DSM_CHECK(cond, DSM_ERR_INVALID_ARG, msg)
+
+extern "C" {
+
+const char* dsm_version(void) { return "dsm_b200 0.1.0 (sm_100a)"; }
+
+size_t dsm_last_error(char* buf, size_t cap) {
+  const std::string& s = last_error();
+  if (buf && cap) {
+    size_t n = std::min(cap - 1, s.size());
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return s.size();
+}
+
+int32_t dsm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+long long dsm_launch_count(void) { return g_launch_count; }
+void dsm_launch_count_reset(void) { g_launch_count = 0; }
+
+void dsm_mimi_spec_v0_1(dsm_mimi_spec* s, int32_t n_q) {
+  if (!s) return;
+  memset(s, 0, sizeof *s);
+  s->n_q = n_q > 0 ? n_q : 16;   // mimi.rs:88: default 16 when unspecified
+  s->bins = 2048, s->qdim = 256, s->dim = 512, s->n_filters = 64;
+  s->ratios[0] = 8, s->ratios[1] = 6, s->ratios[2] = 5, s->ratios[3] = 4;
+  s->kernel_size = 7, s->residual_kernel_size = 3, s->last_kernel_size = 3, s->compress = 2;
+  s->num_heads = 8, s->num_layers = 8, s->dim_feedforward = 2048, s->context = 250;
+  s->max_period = 10000.f, s->ln_eps = 1e-5f, s->downsample_stride = 2;
+  s->with_encoder = 1, s->with_decoder = 1;
+}
+
+void dsm_lm_spec_stt_1b_en_fr(dsm_lm_spec* s) {
+  if (!s) return;
+  memset(s, 0, sizeof *s);
+  s->d_model = 2048, s->num_heads = 16, s->num_layers = 16, s->dim_feedforward = 8192, s->context = 750;
+  s->max_period = 100000.f, s->text_in_vocab_size = 8001, s->text_out_vocab_size = 8000;
+  s->audio_vocab_size = 2049, s->audio_codebooks = 32, s->extra_heads_num = 4, s->extra_heads_dim = 6;
+  s->rms_eps = 1e-8f;
+}
+
+void dsm_lm_spec_stt_2_6b_en(dsm_lm_spec* s) {
+  if (!s) return;
+  memset(s, 0, sizeof *s);
+  s->d_model = 2048, s->num_heads = 32, s->num_layers = 48, s->dim_feedforward = 8192, s->context = 375;
+  s->max_period = 100000.f, s->text_in_vocab_size = 4001, s->text_out_vocab_size = 4000;
+  s->audio_vocab_size = 2049, s->audio_codebooks = 32, s->extra_heads_num = 0, s->extra_heads_dim = 0;
+  s->rms_eps = 1e-8f;
+}
+
+static void require_device(int32_t device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    fail(DSM_ERR_CUDA, "no CUDA device available (%s); dsm_b200 has no CPU fallback", cudaGetErrorString(e));
+  }
+  DSM_CHECK(device >= 0 && device < n, DSM_ERR_INVALID_ARG, "device %d out of range [0, %d)", device, n);
+  cudaDeviceProp p;
+  DSM_CUDA(cudaGetDeviceProperties(&p, device));
+  DSM_CHECK(p.major == 10, DSM_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+            p.major, p.minor);
+}
+
+// ---- Mimi ----------------------------------------------------------------------------------------
+dsm_status dsm_mimi_create(const dsm_mimi_spec* spec, const dsm_weights* weights, int32_t device, int32_t batch_size,
+                           dsm_mimi** out) {
+  return guarded([&] {
+    REQUIRE(spec && out, "spec and out are required");
+    *out = nullptr;
+    require_device(device);
+    std::unique_ptr<MimiImpl> impl(new MimiImpl(*spec, weights, device, batch_size));
+    *out = new dsm_mimi{impl.release()};
+  });
+}
+void dsm_mimi_destroy(dsm_mimi* h) {
+  if (!h) return;
+  delete h->impl;
+  delete h;
+}
+dsm_status dsm_mimi_encode_step(dsm_mimi* h, const float* pcm, const uint8_t* mask, uint32_t* codes, int32_t* produced) {
+  return guarded([&] {
+    REQUIRE(h && pcm, "handle and pcm are required");
+    if (produced) *produced = 0;
+    h->impl->encode_step(pcm, mask, codes);
+    if (produced) *produced = 1;
+  });
+}
+dsm_status dsm_mimi_decode_step(dsm_mimi* h, const uint32_t* codes, const uint8_t* mask, float* pcm, int32_t* produced) {
+  return guarded([&] {
+    REQUIRE(h && codes, "handle and codes are required");
+    if (produced) *produced = 0;
+    h->impl->decode_step(codes, mask, pcm);
+    if (produced) *produced = 1;
+  });
+}
+dsm_status dsm_mimi_last_latent(dsm_mimi* h, float* latent) {
+  return guarded([&] {
+    REQUIRE(h && latent, "handle and latent are required");
+    MimiImpl* m = h->impl;
+    REQUIRE(m->latent, "handle has no encoder");
+    DSM_CUDA(cudaSetDevice(m->device));
+    DSM_CUDA(cudaMemcpyAsync(latent, m->latent, (size_t)m->B * m->spec.dim * 4, cudaMemcpyDefault, m->stream));
+    DSM_CUDA(cudaStreamSynchronize(m->stream));
+  });
+}
+dsm_status dsm_mimi_debug_tensor(dsm_mimi* h, const char* name, float* out, int64_t cap, int64_t* numel) {
+  return guarded([&] {
+    REQUIRE(h && name, "handle and name are required");
+    MimiImpl* m = h->impl;
+    const float* src = nullptr;
+    int64_t n = 0;
+    const std::string s(name);
+    if (s == "seanet_out") src = m->dbg_seanet, n = (int64_t)m->B * 2 * m->spec.dim;
+    else if (s == "transformer_out") src = m->dbg_xfmr, n = (int64_t)m->B * 2 * m->spec.dim;
+    else if (s == "latent") src = m->latent, n = (int64_t)m->B * m->spec.dim;
+    else if (s == "dec_emb") src = m->dec_emb, n = (int64_t)m->B * m->spec.dim;
+    else fail(DSM_ERR_INVALID_ARG, "unknown debug tensor '%s'", name);
+    REQUIRE(src, "that tensor does not exist on this handle");
+    if (numel) *numel = n;
+    if (out) {
+      DSM_CHECK(cap >= n, DSM_ERR_SHAPE, "buffer of %lld floats is too small for %lld", (long long)cap, (long long)n);
+      DSM_CUDA(cudaSetDevice(m->device));
+      DSM_CUDA(cudaMemcpyAsync(out, src, (size_t)n * 4, cudaMemcpyDefault, m->stream));
+      DSM_CUDA(cudaStreamSynchronize(m->stream));
+    }
+  });
+}
+dsm_status dsm_mimi_reset_state(dsm_mimi* h) {
+  return guarded([&] {
+    REQUIRE(h, "handle is required");
+    h->impl->reset_state();
+  });
+}
+dsm_status dsm_mimi_reset_batch_idx(dsm_mimi* h, int32_t b) {
+  return guarded([&] {
+    REQUIRE(h, "handle is required");
+    h->impl->reset_batch_idx(b);
+  });
+}
+dsm_status dsm_mimi_synchronize(dsm_mimi* h) {
+  return guarded([&] {
+    REQUIRE(h, "handle is required");
+    DSM_CUDA(cudaSetDevice(h->impl->device));
+    DSM_CUDA(cudaStreamSynchronize(h->impl->stream));
+  });
+}
+int32_t dsm_mimi_batch_size(const dsm_mimi* h) { return h ? h->impl->B : 0; }
+int32_t dsm_mimi_n_q(const dsm_mimi* h) { return h ? h->impl->spec.n_q : 0; }
+int64_t dsm_mimi_device_bytes(const dsm_mimi* h) { return h ? (int64_t)h->impl->arena.total_bytes() : 0; }
+int64_t dsm_mimi_kv_bytes(const dsm_mimi* h) { return h ? (int64_t)(h->impl->enc_tr.kv_bytes + h->impl->dec_tr.kv_bytes) : 0; }
+
+// ---- LM ------------------------------------------------------------------------------------------
+dsm_status dsm_lm_create(const dsm_lm_spec* spec, const dsm_weights* weights, int32_t device, int32_t batch_size,
+                         dsm_lm** out) {
+  return guarded([&] {
+    REQUIRE(spec && out, "spec and out are required");
+    *out = nullptr;
+    require_device(device);
+    std::unique_ptr<LmImpl> impl(new LmImpl(*spec, weights, device, batch_size));
+    *out = new dsm_lm{impl.release()};
+  });
+}
+void dsm_lm_destroy(dsm_lm* h) {
+  if (!h) return;
+  delete h->impl;
+  delete h;
+}
+dsm_status dsm_lm_forward(dsm_lm* h, const uint32_t* text_ids, const uint32_t* audio_ids, const float* cond,
+                          const uint8_t* mask, float* logits, float* ys) {
+  return guarded([&] {
+    REQUIRE(h, "handle is required");
+    h->impl->forward(text_ids, audio_ids, cond, mask, logits, ys);
+  });
+}
+dsm_status dsm_lm_reset_state(dsm_lm* h) {
+  return guarded([&] {
+    REQUIRE(h, "handle is required");
+    h->impl->reset_state();
+  });
+}
+dsm_status dsm_lm_reset_batch_idx(dsm_lm* h, int32_t b) {
+  return guarded([&] {
+    REQUIRE(h, "handle is required");
+    h->impl->reset_batch_idx(b);
+    DSM_CUDA(cudaStreamSynchronize(h->impl->stream));
+  });
+}
+dsm_status dsm_lm_synchronize(dsm_lm* h) {
+  return guarded([&] {
+    REQUIRE(h, "handle is required");
+    DSM_CUDA(cudaSetDevice(h->impl->device));
+    DSM_CUDA(cudaStreamSynchronize(h->impl->stream));
+  });
+}
+int32_t dsm_lm_text_start_token(const dsm_lm* h) { return h ? h->impl->spec.text_in_vocab_size - 1 : -1; }
+int32_t dsm_lm_audio_pad_token(const dsm_lm* h) { return h ? h->impl->spec.audio_vocab_size - 1 : -1; }
+int32_t dsm_lm_in_audio_codebooks(const dsm_lm* h) { return h ? h->impl->spec.audio_codebooks : 0; }
+int64_t dsm_lm_kv_bytes(const dsm_lm* h) { return h ? (int64_t)h->impl->kv_bytes : 0; }
+int64_t dsm_lm_weight_bytes(const dsm_lm* h) { return h ? (int64_t)h->impl->weight_bytes : 0; }
+
+// ---- ASR -----------------------------------------------------------------------------------------
+dsm_status dsm_asr_create(dsm_mimi* mimi, dsm_lm* lm, int32_t delay, float temperature, dsm_asr** out) {
+  return guarded([&] {
+    REQUIRE(lm && out, "lm and out are required");
+    *out = nullptr;
+    std::unique_ptr<AsrImpl> impl(new AsrImpl(mimi ? mimi->impl : nullptr, lm->impl, delay, temperature));
+    *out = new dsm_asr{impl.release(), mimi, lm};
+  });
+}
+void dsm_asr_destroy(dsm_asr* h) {
+  if (!h) return;
+  delete h->impl;
+  delete h;
+}
+dsm_status dsm_asr_step_pcm(dsm_asr* h, const float* pcm, const uint8_t* mask, uint32_t* text_tokens) {
+  return guarded([&] {
+    REQUIRE(h && pcm, "handle and pcm are required");
+    h->impl->step(pcm, nullptr, mask, text_tokens);
+  });
+}
+dsm_status dsm_asr_step_tokens(dsm_asr* h, const uint32_t* codes, const uint8_t* mask, uint32_t* text_tokens) {
+  return guarded([&] {
+    REQUIRE(h && codes, "handle and codes are required");
+    h->impl->step(nullptr, codes, mask, text_tokens);
+  });
+}
+int32_t dsm_asr_msg_count(const dsm_asr* h) { return h ? (int32_t)h->impl->msgs.size() : 0; }
+dsm_status dsm_asr_msg_get(const dsm_asr* h, int32_t i, dsm_asr_msg* out) {
+  return guarded([&] {
+    REQUIRE(h && out, "handle and out are required");
+    const AsrImpl* a = h->impl;
+    DSM_CHECK(i >= 0 && i < (int32_t)a->msgs.size(), DSM_ERR_INVALID_ARG, "message index %d out of range", i);
+    const AsrMsgStore& m = a->msgs[i];
+    memset(out, 0, sizeof *out);
+    out->kind = m.kind, out->batch_idx = m.batch_idx, out->step_idx = m.step_idx, out->time = m.time;
+    out->n_tokens = (int32_t)m.tokens.size();
+    out->tokens = m.tokens.empty() ? nullptr : m.tokens.data();
+    out->prs = m.kind == DSM_MSG_STEP ? a->prs_copy.data() : nullptr;
+  });
+}
+dsm_status dsm_asr_reset(dsm_asr* h) {
+  return guarded([&] {
+    REQUIRE(h, "handle is required");
+    h->impl->reset();
+  });
+}
+dsm_status dsm_asr_reset_batch_idx(dsm_asr* h, int32_t b) {
+  return guarded([&] {
+    REQUIRE(h, "handle is required");
+    h->impl->reset_batch_idx(b);
+  });
+}
+int32_t dsm_asr_batch_size(const dsm_asr* h) { return h ? h->impl->B : 0; }
+int32_t dsm_asr_model_step_idx(const dsm_asr* h) { return h ? h->impl->model_step_idx : 0; }
+int32_t dsm_asr_delay_in_tokens(const dsm_asr* h) { return h ? h->impl->delay : 0; }
+dsm_status dsm_asr_last_logits(dsm_asr* h, float* logits) {
+  return guarded([&] {
+    REQUIRE(h && logits, "handle and logits are required");
+    LmImpl* l = h->impl->lm;
+    DSM_CUDA(cudaSetDevice(l->device));
+    DSM_CUDA(cudaMemcpyAsync(logits, l->logits, (size_t)l->B * l->spec.text_out_vocab_size * 4, cudaMemcpyDefault, l->stream));
+    DSM_CUDA(cudaStreamSynchronize(l->stream));
+  });
+}
+dsm_status dsm_asr_last_step_ms(dsm_asr* h, float out[3]) {
+  return guarded([&] {
+    REQUIRE(h && out, "handle and out are required");
+    for (int i = 0; i < 3; ++i) out[i] = h->impl->last_ms[i];
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// Shared helpers for the dsm_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/dsm_b200.h"
+
+namespace dsm {
+
+// ---- error plumbing: C++ exceptions inside, status codes at the ABI -------------------------
+struct Error : std::runtime_error {
+  dsm_status code;
+  Error(dsm_status c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& msg);
+
+[[noreturn]] inline void fail(dsm_status code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Error(code, buf);
+}
+
+#define DSM_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      ::dsm::fail(_e == cudaErrorMemoryAllocation ? DSM_ERR_OOM : DSM_ERR_CUDA,                \
+                  "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define DSM_CHECK(cond, code, ...) \
+  do {                             \
+    if (!(cond)) ::dsm::fail(code, __VA_ARGS__); \
+  } while (0)
+
+// Launch-count bookkeeping (bench.py reports "gpu_launches").
+extern thread_local long long g_launch_count;
+#define DSM_LAUNCHED() (++::dsm::g_launch_count)
+
+inline void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fail(DSM_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  DSM_LAUNCHED();
+}
+
+// Row addressing shared by every row-wise kernel: logical row m = b * T + t lives at
+// base + b * stride_b + t * stride_t (elements).  Lets a layer read a window of, or write into, a
+// neighbour's state-carrying buffer without copies.
+struct RowMap {
+  int T;
+  long long stride_b;
+  long long stride_t;
+  __host__ __device__ long long off(int m) const {
+    int b = m / T, t = m - b * T;
+    return b * stride_b + t * stride_t;
+  }
+};
+inline RowMap dense_rows(int T, long long row_len) { return RowMap{T, (long long)T * row_len, row_len}; }
+
+template <typename T>
+inline T ceil_div(T a, T b) {
+  return (a + b - 1) / b;
+}
+
+// ---- device helpers --------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+}  // namespace dsm

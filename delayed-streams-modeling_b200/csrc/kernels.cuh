@@ -1,0 +1,95 @@
+// Launch wrappers for the hand-written kernels (definitions in mimi_kernels.cu / lm_kernels.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace dsm {
+
+// ---- ring KV bookkeeping (kv_cache.rs:119-237 without the host round trip) -------------------
+// Per stream: reads mask[b]; publishes the pre-advance write index / position and the rope base
+// position for this step; advances (index, position) by t when active.
+struct RingState {
+  uint32_t* positions;  // [B] absolute position (can exceed context)
+  uint32_t* indices;    // [B] next write slot
+  uint32_t* cur_index;  // [B] slot the first new token is written to this step
+  uint32_t* cur_pos;    // [B] position of the first new token this step
+  uint32_t* rope_pos;   // [B] positions[b] as the reference reads it AFTER the advance
+};
+void launch_ring_advance(const RingState& rs, const uint8_t* mask, int B, int t, int context, cudaStream_t st);
+
+// ---- SEANet ------------------------------------------------------------------------------------
+// First encoder conv (C_in = 1): x(t) = t < S ? state[b, t] : pcm[b, t - S]; writes raw and ELU copies.
+void launch_init_conv(const float* pcm, const float* state, int S, const float* w /*[C,k]*/, const float* bias,
+                      int B, int T, int C, int k, float* out_raw, RowMap raw_map, float* out_act, RowMap act_map,
+                      cudaStream_t st);
+// Last decoder conv (C_out = 1): pcm[b, t] = bias + sum_{j,ci} w[j*C+ci] * x[b, t+j, ci] (x already ELU'd).
+void launch_final_conv(const float* x, RowMap x_map /*row = (b, t)*/, const float* w /*[k*C]*/, const float* bias,
+                       int B, int T, int C, int k, float* pcm, cudaStream_t st);
+
+// One entry per state-carrying buffer: for active streams copy `count` floats from src to dst.
+struct CommitEntry {
+  float* dst;
+  const float* src;
+  long long dst_stride_b, src_stride_b;
+  int count;
+  int zero_if_inactive_first;  // replicate-padded layer: an inactive stream's state is zeroed on the first step
+};
+void launch_commit_state(const CommitEntry* entries_dev, int n_entries, int max_count, const uint8_t* mask,
+                         int* first_step_flag, int B, cudaStream_t st);
+// Replicate left pad on a module's first step (conv.rs:318-327 with PadMode::Replicate): rows [0,S) <- row S.
+void launch_replicate_pad(float* x, long long stride_b, int S, int C, const int* first_step_flag, int B,
+                          cudaStream_t st);
+// Zero every entry's state for streams [b0, b0 + nb) (per-slot reset, conv.rs:274-281; reset_state).
+void launch_zero_rows(const CommitEntry* entries_dev, int n_entries, int b0, int nb, cudaStream_t st);
+
+// ---- codec transformer (f32) ---------------------------------------------------------------------
+void launch_layernorm(const float* x, RowMap x_map, const float* w, const float* b, float eps, int M, int D,
+                      float* out /*dense [M,D]*/, cudaStream_t st);
+// qkv [M, 3*H*D] (M = B*t) -> q rotated in place; rotated k and v scattered into the rings [B,H,ctx,D].
+void launch_rope_scatter_f32(float* qkv, const RingState& rs, const uint8_t* mask, int B, int t, int H, int D,
+                             int context, const float* inv_freq /*[D/2]*/, float* k_ring, float* v_ring, cudaStream_t st);
+// out[m, h*D + d] = softmax(q . K^T * D^-0.5 + mask) . V over the ring, visibility by stored position.
+void launch_codec_attention(const float* qkv, const RingState& rs, const uint8_t* mask, int B, int t, int H, int D,
+                            int context, const float* k_ring, const float* v_ring, float* out, cudaStream_t st);
+
+// ---- RVQ -----------------------------------------------------------------------------------------
+// scores [B, bins] = c2 - x.E^T (from the GEMM); idx = first argmin; residual[b,:] -= E[idx,:]; codes[b*n_q+q] = idx.
+void launch_rvq_select(const float* scores, int B, int bins, const float* embedding /*[bins,qdim]*/, int qdim,
+                       float* residual, long long res_stride, uint32_t* codes, int n_q, int q, cudaStream_t st);
+// decode: out[b, :] = sum_q E_q[codes[b,q], :] over q in [q0, q1)  (quantization.rs:231-248)
+void launch_rvq_gather_sum(const uint32_t* codes, int n_q, int q0, int q1, const float* embeddings /*[n_q][bins][qdim]*/,
+                           int bins, int qdim, int B, float* out, cudaStream_t st);
+// depthwise conv-transpose k=2s (ConvTrUpsample1d, conv.rs:558-606), one input frame -> s frames,
+// carried state = previous input row.  x [B, C]; state [B, C]; out rows (b, r) r < s.
+void launch_upsample_dw(const float* x, const float* state, const float* w /*[C, 2s]*/, int B, int C, int s,
+                        float* out, RowMap out_map, cudaStream_t st);
+
+// ---- LM (bf16 operands, f32 accumulate) -----------------------------------------------------------
+void launch_embed_sum(const uint32_t* text_ids, const uint32_t* audio_ids, int n_cb, const __nv_bfloat16* text_emb,
+                      int text_vocab, const __nv_bfloat16* audio_emb /*[n_cb][audio_vocab][D]*/, int audio_vocab,
+                      const float* cond, int B, int D, float* x, cudaStream_t st);
+void launch_rmsnorm(const float* x, const float* alpha, float eps, int B, int D, __nv_bfloat16* out_bf16,
+                    float* out_f32, cudaStream_t st);
+// qkv f32 [B, 3*H*D] -> q bf16 [B, H*D] (rotated); rotated k, v -> bf16 rings [B,H,ctx,D] at cur_index[b].
+void launch_rope_scatter_bf16(const float* qkv, const RingState& rs, int B, int H, int D, int context,
+                              const float* inv_freq /*[D/2]*/,
+                              __nv_bfloat16* q_out, __nv_bfloat16* k_ring, __nv_bfloat16* v_ring, cudaStream_t st);
+void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint8_t* mask, int B, int H, int D,
+                         int context, const __nv_bfloat16* k_ring, const __nv_bfloat16* v_ring,
+                         __nv_bfloat16* out, cudaStream_t st);
+// h f32 [B, 2*Hd] -> g bf16 [B, Hd] = silu(h[:, :Hd]) * h[:, Hd:]   (batched_transformer.rs:170-176)
+void launch_silu_gate(const float* h, int B, int Hd, __nv_bfloat16* g, cudaStream_t st);
+// greedy sampling (asr.rs:208-210): first argmax over logits [B, V]
+void launch_argmax(const float* logits, int B, int V, uint32_t* tokens, cudaStream_t st);
+// extra heads (lm.rs:948-955 + asr.rs:195-206): prs[h*B + b] = softmax(W_h . ys[b])[0]
+void launch_extra_heads(const __nv_bfloat16* ys, const __nv_bfloat16* w /*[nh][dim][D]*/, int nh, int dim, int B, int D,
+                        float* prs, cudaStream_t st);
+// token feed (asr.rs:133-145,172-176): lm_audio_in = first_step[b] ? pad : next_cb[b]; lm_text_in =
+// first_step[b] ? start : text_tok[b]
+void launch_asr_prepare(const uint32_t* next_cb, const uint8_t* first_step, const uint32_t* text_tok, uint32_t pad,
+                        uint32_t start, int B, int n_cb, uint32_t* lm_audio_in, uint32_t* lm_text_in, cudaStream_t st);
+// state update for active streams (asr.rs:177-183,221-226): next_cb <- codes, text_tok <- sampled, first_step <- 0
+void launch_asr_commit(const uint32_t* codes, const uint8_t* mask, const uint32_t* sampled, int B, int n_cb,
+                       uint32_t* next_cb, uint32_t* text_tok, uint8_t* first_step, cudaStream_t st);
+
+}  // namespace dsm

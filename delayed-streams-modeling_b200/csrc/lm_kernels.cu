@@ -1,0 +1,417 @@
+// Hand-written kernels of the delayed-streams LM step that are not GEMMs: embedding sum, RMSNorm,
+// RoPE + ring scatter, single-query ring attention (bf16 KV, f32 math), SiLU gate, greedy argmax,
+// VAD extra heads, and the ASR token feed / commit.
+#include "kernels.cuh"
+
+namespace dsm {
+
+// ================================================================================================
+// emb = E_text[t] + sum_i E_audio_i[c_i] (+ cond)   (lm.rs:983-1000).  f32 accumulation, in the
+// reference's order.  One CTA per stream, 8 contiguous bf16 per thread-load.
+// ================================================================================================
+__global__ void __launch_bounds__(256) embed_sum_kernel(const uint32_t* __restrict__ text_ids,
+                                                         const uint32_t* __restrict__ audio_ids, int n_cb,
+                                                         const __nv_bfloat16* __restrict__ text_emb, int text_vocab,
+                                                         const __nv_bfloat16* __restrict__ audio_emb, int audio_vocab,
+                                                         const float* __restrict__ cond, int D, float* __restrict__ x) {
+  const int b = blockIdx.x;
+  uint32_t tid_text = text_ids[b];
+  if (tid_text >= (uint32_t)text_vocab) tid_text = text_vocab - 1;
+  for (int c = threadIdx.x * 8; c < D; c += blockDim.x * 8) {
+    float acc[8];
+    {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(text_emb + (long long)tid_text * D + c));
+      acc[0] = bf16_lo(u.x), acc[1] = bf16_hi(u.x), acc[2] = bf16_lo(u.y), acc[3] = bf16_hi(u.y);
+      acc[4] = bf16_lo(u.z), acc[5] = bf16_hi(u.z), acc[6] = bf16_lo(u.w), acc[7] = bf16_hi(u.w);
+    }
+    for (int i = 0; i < n_cb; ++i) {
+      uint32_t id = audio_ids[(long long)b * n_cb + i];
+      if (id >= (uint32_t)audio_vocab) id = audio_vocab - 1;
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(audio_emb + ((long long)i * audio_vocab + id) * D + c));
+      acc[0] += bf16_lo(u.x), acc[1] += bf16_hi(u.x), acc[2] += bf16_lo(u.y), acc[3] += bf16_hi(u.y);
+      acc[4] += bf16_lo(u.z), acc[5] += bf16_hi(u.z), acc[6] += bf16_lo(u.w), acc[7] += bf16_hi(u.w);
+    }
+    if (cond) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += cond[c + j];
+    }
+    float* o = x + (long long)b * D + c;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+void launch_embed_sum(const uint32_t* text_ids, const uint32_t* audio_ids, int n_cb, const __nv_bfloat16* text_emb,
+                      int text_vocab, const __nv_bfloat16* audio_emb, int audio_vocab, const float* cond, int B, int D,
+                      float* x, cudaStream_t st) {
+  DSM_CHECK(D % 8 == 0, DSM_ERR_UNSUPPORTED, "embed_sum: D=%d", D);
+  embed_sum_kernel<<<B, 256, 0, st>>>(text_ids, audio_ids, n_cb, text_emb, text_vocab, audio_emb, audio_vocab, cond, D, x);
+  check_launch("embed_sum");
+}
+
+// ================================================================================================
+// RMSNorm (batched_transformer.rs:181-198, eps 1e-8): x * rsqrt(mean(x^2) + eps) * alpha, f32 math,
+// bf16 (GEMM operand) and optional f32 outputs.  One CTA per stream.
+// ================================================================================================
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
+                                                       float eps, int D, __nv_bfloat16* __restrict__ out_bf16,
+                                                       float* __restrict__ out_f32) {
+  __shared__ float s_part[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* row = x + (long long)b * D;
+  float ss = 0.f;
+  for (int c = tid * 4; c < D; c += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(row + c);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) s_part[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += s_part[w];
+  const float r = rsqrtf(tot / (float)D + eps);
+  for (int c = tid * 4; c < D; c += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(row + c);
+    float4 a = *reinterpret_cast<const float4*>(alpha + c);
+    float4 o = make_float4(v.x * r * a.x, v.y * r * a.y, v.z * r * a.z, v.w * r * a.w);
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + (long long)b * D + c) = o;
+    if (out_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(out_bf16 + (long long)b * D + c) = u;
+    }
+  }
+}
+
+void launch_rmsnorm(const float* x, const float* alpha, float eps, int B, int D, __nv_bfloat16* out_bf16,
+                    float* out_f32, cudaStream_t st) {
+  DSM_CHECK(D % 4 == 0, DSM_ERR_UNSUPPORTED, "rmsnorm: D=%d", D);
+  rmsnorm_kernel<<<B, 256, 0, st>>>(x, alpha, eps, D, out_bf16, out_f32);
+  check_launch("rmsnorm");
+}
+
+// ================================================================================================
+// RoPE in f32 (transformer.rs:372-378) on q, k; q -> bf16 [B, H*D]; k, v -> bf16 ring slot cur_index[b].
+// ================================================================================================
+__global__ void __launch_bounds__(256) rope_scatter_bf16_kernel(const float* __restrict__ qkv, RingState rs, int H,
+                                                                 int D, int context, const float* __restrict__ inv_freq,
+                                                                 __nv_bfloat16* __restrict__ q_out,
+                                                                 __nv_bfloat16* __restrict__ k_ring,
+                                                                 __nv_bfloat16* __restrict__ v_ring) {
+  const int b = blockIdx.x;
+  const int slot = (int)rs.cur_index[b];
+  const float pos = (float)rs.rope_pos[b];
+  const int HD = H * D, half = D / 2;
+  const float* row = qkv + (long long)b * 3 * HD;
+  for (int i = threadIdx.x; i < H * half; i += blockDim.x) {
+    const int h = i / half, p = i - h * half;
+    float sn, cs;
+    sincosf(pos * inv_freq[p], &sn, &cs);
+    const float2 q = *reinterpret_cast<const float2*>(row + h * D + 2 * p);
+    const float2 k = *reinterpret_cast<const float2*>(row + HD + h * D + 2 * p);
+    const float2 v = *reinterpret_cast<const float2*>(row + 2 * HD + h * D + 2 * p);
+    *reinterpret_cast<__nv_bfloat162*>(q_out + (long long)b * HD + h * D + 2 * p) =
+        __floats2bfloat162_rn(q.x * cs - q.y * sn, q.x * sn + q.y * cs);
+    const long long o = (((long long)b * H + h) * context + slot) * D + 2 * p;
+    *reinterpret_cast<__nv_bfloat162*>(k_ring + o) = __floats2bfloat162_rn(k.x * cs - k.y * sn, k.x * sn + k.y * cs);
+    *reinterpret_cast<__nv_bfloat162*>(v_ring + o) = __floats2bfloat162_rn(v.x, v.y);
+  }
+}
+
+void launch_rope_scatter_bf16(const float* qkv, const RingState& rs, int B, int H, int D, int context,
+                              const float* inv_freq, __nv_bfloat16* q_out, __nv_bfloat16* k_ring,
+                              __nv_bfloat16* v_ring, cudaStream_t st) {
+  rope_scatter_bf16_kernel<<<B, 256, 0, st>>>(qkv, rs, H, D, context, inv_freq, q_out, k_ring, v_ring);
+  check_launch("rope_scatter_bf16");
+}
+
+// ================================================================================================
+// Single-query attention over the per-stream ring (batched_transformer.rs:107-113, mask of
+// kv_cache.rs:130-170: slot j visible iff j <= position before the advance).  THE dominant kernel of
+// the step: per (stream, head) it streams ctx*D*2 bf16 of K and of V from HBM exactly once.
+// One CTA (4 warps) per (stream, head).  A key row of D bf16 is covered by D/8 lanes x 16 B, so one
+// warp-wide load instruction fetches 32*16 B = 512 contiguous bytes (256/D keys... 2 keys at D=128,
+// 4 at D=64); loads are unrolled UNROLL deep to keep >= 4 KB per warp in flight.
+// ================================================================================================
+template <int D, int UNROLL>
+__global__ void __launch_bounds__(128) lm_attention_kernel(const __nv_bfloat16* __restrict__ q, RingState rs,
+                                                            const uint8_t* __restrict__ mask, int H, int context,
+                                                            const __nv_bfloat16* __restrict__ k_ring,
+                                                            const __nv_bfloat16* __restrict__ v_ring,
+                                                            __nv_bfloat16* __restrict__ out) {
+  constexpr int LPK = D / 8;          // lanes per key
+  constexpr int KPW = 32 / LPK;       // keys per warp-load
+  constexpr int NW = 4;
+  extern __shared__ float sm[];
+  float* sc = sm;                     // [context]
+  float* red = sm + context;          // [NW][D]
+  __shared__ float s_red[NW];
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int HD = H * D;
+  __nv_bfloat16* orow = out + (long long)b * HD + h * D;
+  const bool active = mask ? mask[b] != 0 : true;
+  if (!active) {
+    // an inactive stream's output is never consumed (asr.rs:221-223); skip the ring read
+    for (int d = tid; d < D; d += blockDim.x) orow[d] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const uint32_t p0 = rs.cur_pos[b];
+  const int n = p0 + 1 < (uint32_t)context ? (int)(p0 + 1) : context;   // visible slots are [0, n)
+  const int c8 = lane % LPK, sub = lane / LPK;
+  const float scale = rsqrtf((float)D);
+
+  float qf[8];
+  {
+    uint4 u = *reinterpret_cast<const uint4*>(q + (long long)b * HD + h * D + c8 * 8);
+    qf[0] = bf16_lo(u.x) * scale, qf[1] = bf16_hi(u.x) * scale, qf[2] = bf16_lo(u.y) * scale, qf[3] = bf16_hi(u.y) * scale;
+    qf[4] = bf16_lo(u.z) * scale, qf[5] = bf16_hi(u.z) * scale, qf[6] = bf16_lo(u.w) * scale, qf[7] = bf16_hi(u.w) * scale;
+  }
+  const __nv_bfloat16* kb = k_ring + ((long long)b * H + h) * context * D;
+  const __nv_bfloat16* vb = v_ring + ((long long)b * H + h) * context * D;
+
+  // ---- scores ----
+  for (int j0 = warp * KPW * UNROLL; j0 < n; j0 += NW * KPW * UNROLL) {
+    uint4 kv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int j = j0 + u * KPW + sub;
+      kv[u] = j < n ? __ldg(reinterpret_cast<const uint4*>(kb + (long long)j * D + c8 * 8)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      float s = qf[0] * bf16_lo(kv[u].x);
+      s = fmaf(qf[1], bf16_hi(kv[u].x), s);
+      s = fmaf(qf[2], bf16_lo(kv[u].y), s);
+      s = fmaf(qf[3], bf16_hi(kv[u].y), s);
+      s = fmaf(qf[4], bf16_lo(kv[u].z), s);
+      s = fmaf(qf[5], bf16_hi(kv[u].z), s);
+      s = fmaf(qf[6], bf16_lo(kv[u].w), s);
+      s = fmaf(qf[7], bf16_hi(kv[u].w), s);
+#pragma unroll
+      for (int o = LPK / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const int j = j0 + u * KPW + sub;
+      if (c8 == 0 && j < n) sc[j] = s;
+    }
+  }
+  __syncthreads();
+
+  // ---- softmax (f32) ----
+  float mx = -INFINITY;
+  for (int j = tid; j < n; j += blockDim.x) mx = fmaxf(mx, sc[j]);
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = tid; j < n; j += blockDim.x) {
+    const float e = __expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  const float inv = 1.f / (s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+
+  // ---- P.V ----
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int j0 = warp * KPW * UNROLL; j0 < n; j0 += NW * KPW * UNROLL) {
+    uint4 vv[UNROLL];
+    float pj[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int j = j0 + u * KPW + sub;
+      const bool ok = j < n;
+      vv[u] = ok ? __ldg(reinterpret_cast<const uint4*>(vb + (long long)j * D + c8 * 8)) : make_uint4(0, 0, 0, 0);
+      pj[u] = ok ? sc[j] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      acc[0] = fmaf(pj[u], bf16_lo(vv[u].x), acc[0]);
+      acc[1] = fmaf(pj[u], bf16_hi(vv[u].x), acc[1]);
+      acc[2] = fmaf(pj[u], bf16_lo(vv[u].y), acc[2]);
+      acc[3] = fmaf(pj[u], bf16_hi(vv[u].y), acc[3]);
+      acc[4] = fmaf(pj[u], bf16_lo(vv[u].z), acc[4]);
+      acc[5] = fmaf(pj[u], bf16_hi(vv[u].z), acc[5]);
+      acc[6] = fmaf(pj[u], bf16_lo(vv[u].w), acc[6]);
+      acc[7] = fmaf(pj[u], bf16_hi(vv[u].w), acc[7]);
+    }
+  }
+  // fold the KPW key sub-groups of a warp, then the warps
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = LPK; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp * D + c8 * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int d = tid; d < D; d += blockDim.x) {
+    const float v = (red[d] + red[D + d] + red[2 * D + d] + red[3 * D + d]) * inv;
+    orow[d] = __float2bfloat16_rn(v);
+  }
+}
+
+void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint8_t* mask, int B, int H, int D,
+                         int context, const __nv_bfloat16* k_ring, const __nv_bfloat16* v_ring, __nv_bfloat16* out,
+                         cudaStream_t st) {
+  size_t smem = (size_t)(context + 4 * D) * sizeof(float);
+  if (D == 128)
+    lm_attention_kernel<128, 8><<<B * H, 128, smem, st>>>(q, rs, mask, H, context, k_ring, v_ring, out);
+  else if (D == 64)
+    lm_attention_kernel<64, 8><<<B * H, 128, smem, st>>>(q, rs, mask, H, context, k_ring, v_ring, out);
+  else
+    fail(DSM_ERR_UNSUPPORTED, "lm_attention: head_dim %d (64 or 128)", D);
+  check_launch("lm_attention");
+}
+
+// ================================================================================================
+// SiLU gate (batched_transformer.rs:170-176): contiguous halves, gate first.
+// ================================================================================================
+__global__ void silu_gate_kernel(const float* __restrict__ h, int Hd, __nv_bfloat16* __restrict__ g, long long total4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int per_row = Hd / 4;
+  const long long b = i / per_row;
+  const int c = (int)(i - b * per_row) * 4;
+  const float4 a = *reinterpret_cast<const float4*>(h + b * 2 * Hd + c);
+  const float4 v = *reinterpret_cast<const float4*>(h + b * 2 * Hd + Hd + c);
+  __nv_bfloat162 lo = __floats2bfloat162_rn(silu(a.x) * v.x, silu(a.y) * v.y);
+  __nv_bfloat162 hi = __floats2bfloat162_rn(silu(a.z) * v.z, silu(a.w) * v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(g + b * Hd + c) = u;
+}
+void launch_silu_gate(const float* h, int B, int Hd, __nv_bfloat16* g, cudaStream_t st) {
+  DSM_CHECK(Hd % 4 == 0, DSM_ERR_UNSUPPORTED, "silu_gate: hidden=%d", Hd);
+  const long long total4 = (long long)B * Hd / 4;
+  silu_gate_kernel<<<(unsigned)ceil_div(total4, 256LL), 256, 0, st>>>(h, Hd, g, total4);
+  check_launch("silu_gate");
+}
+
+// ================================================================================================
+// greedy argmax over the text logits (asr.rs:208-210), first index on ties.
+// ================================================================================================
+__global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ logits, int V, uint32_t* __restrict__ tokens) {
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* row = logits + (long long)b * V;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = tid; j < V; j += blockDim.x) {
+    const float v = row[j];
+    if (v > best) best = v, bi = j;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
+  }
+  if ((tid & 31) == 0) s_val[tid >> 5] = best, s_idx[tid >> 5] = bi;
+  __syncthreads();
+  if (tid == 0) {
+    best = s_val[0], bi = s_idx[0];
+    for (int w = 1; w < 8; ++w)
+      if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) best = s_val[w], bi = s_idx[w];
+    tokens[b] = (bi < 0 || bi >= V) ? 0u : (uint32_t)bi;
+  }
+}
+void launch_argmax(const float* logits, int B, int V, uint32_t* tokens, cudaStream_t st) {
+  argmax_kernel<<<B, 256, 0, st>>>(logits, V, tokens);
+  check_launch("argmax");
+}
+
+// ================================================================================================
+// extra (VAD) heads: nh x dim tiny GEMV + softmax, class 0 (lm.rs:948-955, asr.rs:195-206).
+// One CTA per stream, one warp per (head, class) output.
+// ================================================================================================
+__global__ void __launch_bounds__(256) extra_heads_kernel(const __nv_bfloat16* __restrict__ ys,
+                                                           const __nv_bfloat16* __restrict__ w, int nh, int dim, int B,
+                                                           int D, float* __restrict__ prs) {
+  extern __shared__ float s_logit[];  // [nh*dim]
+  const int b = blockIdx.x, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const __nv_bfloat16* y = ys + (long long)b * D;
+  for (int o = warp; o < nh * dim; o += blockDim.x / 32) {
+    const __nv_bfloat16* wr = w + (long long)o * D;
+    float acc = 0.f;
+    for (int c = lane * 8; c < D; c += 256) {
+      const uint4 a = *reinterpret_cast<const uint4*>(y + c);
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(wr + c));
+      acc = fmaf(bf16_lo(a.x), bf16_lo(q.x), acc), acc = fmaf(bf16_hi(a.x), bf16_hi(q.x), acc);
+      acc = fmaf(bf16_lo(a.y), bf16_lo(q.y), acc), acc = fmaf(bf16_hi(a.y), bf16_hi(q.y), acc);
+      acc = fmaf(bf16_lo(a.z), bf16_lo(q.z), acc), acc = fmaf(bf16_hi(a.z), bf16_hi(q.z), acc);
+      acc = fmaf(bf16_lo(a.w), bf16_lo(q.w), acc), acc = fmaf(bf16_hi(a.w), bf16_hi(q.w), acc);
+    }
+    acc = warp_sum(acc);
+    // the reference's head output is a bf16 tensor, widened to f32 before the softmax (asr.rs:199-200)
+    if (lane == 0) s_logit[o] = __bfloat162float(__float2bfloat16_rn(acc));
+  }
+  __syncthreads();
+  if (threadIdx.x < nh) {
+    const float* l = s_logit + threadIdx.x * dim;
+    float mx = l[0];
+    for (int i = 1; i < dim; ++i) mx = fmaxf(mx, l[i]);
+    float sum = 0.f;
+    for (int i = 0; i < dim; ++i) sum += expf(l[i] - mx);
+    prs[(long long)threadIdx.x * B + b] = expf(l[0] - mx) / sum;
+  }
+}
+void launch_extra_heads(const __nv_bfloat16* ys, const __nv_bfloat16* w, int nh, int dim, int B, int D, float* prs,
+                        cudaStream_t st) {
+  DSM_CHECK(D % 256 == 0 && nh <= 256, DSM_ERR_UNSUPPORTED, "extra_heads: D=%d nh=%d", D, nh);
+  extra_heads_kernel<<<B, 256, nh * dim * sizeof(float), st>>>(ys, w, nh, dim, B, D, prs);
+  check_launch("extra_heads");
+}
+
+// ================================================================================================
+// ASR token feed / commit (asr.rs:133-145, 168-183, 218-226)
+// ================================================================================================
+__global__ void asr_prepare_kernel(const uint32_t* __restrict__ next_cb, const uint8_t* __restrict__ first_step,
+                                   const uint32_t* __restrict__ text_tok, uint32_t pad, uint32_t start, int B, int n_cb,
+                                   uint32_t* __restrict__ lm_audio_in, uint32_t* __restrict__ lm_text_in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n_cb) return;
+  const int b = i / n_cb;
+  const bool first = first_step[b] != 0;
+  lm_audio_in[i] = first ? pad : next_cb[i];
+  if (i == b * n_cb) lm_text_in[b] = first ? start : text_tok[b];
+}
+void launch_asr_prepare(const uint32_t* next_cb, const uint8_t* first_step, const uint32_t* text_tok, uint32_t pad,
+                        uint32_t start, int B, int n_cb, uint32_t* lm_audio_in, uint32_t* lm_text_in, cudaStream_t st) {
+  asr_prepare_kernel<<<ceil_div(B * n_cb, 256), 256, 0, st>>>(next_cb, first_step, text_tok, pad, start, B, n_cb,
+                                                             lm_audio_in, lm_text_in);
+  check_launch("asr_prepare");
+}
+
+__global__ void asr_commit_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict__ mask,
+                                  const uint32_t* __restrict__ sampled, int B, int n_cb, uint32_t* __restrict__ next_cb,
+                                  uint32_t* __restrict__ text_tok, uint8_t* __restrict__ first_step) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n_cb) return;
+  const int b = i / n_cb;
+  if (mask && !mask[b]) return;
+  next_cb[i] = codes[i];
+  if (i == b * n_cb) {
+    text_tok[b] = sampled[b];
+    first_step[b] = 0;
+  }
+}
+void launch_asr_commit(const uint32_t* codes, const uint8_t* mask, const uint32_t* sampled, int B, int n_cb,
+                       uint32_t* next_cb, uint32_t* text_tok, uint8_t* first_step, cudaStream_t st) {
+  asr_commit_kernel<<<ceil_div(B * n_cb, 256), 256, 0, st>>>(codes, mask, sampled, B, n_cb, next_cb, text_tok, first_step);
+  check_launch("asr_commit");
+}
+
+}  // namespace dsm

@@ -1,0 +1,263 @@
+#include "runtime.cuh"
+
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace dsm {
+
+thread_local long long g_launch_count = 0;
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const std::string& last_error() { return g_last_error; }
+
+// ---- Arena -------------------------------------------------------------------------------------
+Arena::~Arena() {
+  for (void* p : dev_) cudaFree(p);
+  for (void* p : pinned_) cudaFreeHost(p);
+}
+
+void* Arena::alloc_bytes(size_t bytes, bool zero) {
+  if (bytes == 0) bytes = 16;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    fail(DSM_ERR_OOM, "cudaMalloc of %zu bytes failed: %s (handle already holds %zu bytes)", bytes,
+         cudaGetErrorString(e), total_);
+  }
+  dev_.push_back(p);
+  total_ += bytes;
+  if (zero) DSM_CUDA(cudaMemset(p, 0, bytes));
+  return p;
+}
+
+void* Arena::alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  DSM_CUDA(cudaMallocHost(&p, bytes ? bytes : 16));
+  pinned_.push_back(p);
+  return p;
+}
+
+// ---- WeightTable -------------------------------------------------------------------------------
+WeightTable::WeightTable(const dsm_weights* w) {
+  if (!w) return;
+  for (int64_t i = 0; i < w->count; ++i) {
+    const dsm_tensor& t = w->tensors[i];
+    if (t.name && t.data) map_[t.name] = &t;
+  }
+}
+
+static size_t numel(const dsm_tensor* t) {
+  size_t n = 1;
+  for (int i = 0; i < t->ndim; ++i) n *= (size_t)t->shape[i];
+  return n;
+}
+
+const dsm_tensor* WeightTable::find(const std::string& name) const {
+  auto it = map_.find(name);
+  if (it == map_.end()) fail(DSM_ERR_MISSING_WEIGHT, "missing weight tensor '%s'", name.c_str());
+  return it->second;
+}
+
+static inline float half_to_float(uint16_t h) {
+  uint32_t sign = (uint32_t)(h & 0x8000) << 16, exp = (h >> 10) & 0x1f, man = h & 0x3ff, u;
+  if (exp == 0) {
+    if (man == 0) u = sign;
+    else {
+      int e = -1;
+      do { man <<= 1; ++e; } while (!(man & 0x400));
+      u = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3ff) << 13);
+    }
+  } else if (exp == 31) u = sign | 0x7f800000u | (man << 13);
+  else u = sign | ((exp + 112) << 23) | (man << 13);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+std::vector<float> WeightTable::f32(const std::string& name, size_t expect_numel) const {
+  const dsm_tensor* t = find(name);
+  const size_t n = numel(t);
+  DSM_CHECK(n == expect_numel, DSM_ERR_SHAPE, "weight '%s' has %zu elements, expected %zu", name.c_str(), n, expect_numel);
+  std::vector<float> out(n);
+  if (t->dtype == DSM_F32) memcpy(out.data(), t->data, n * 4);
+  else if (t->dtype == DSM_BF16) {
+    const uint16_t* s = static_cast<const uint16_t*>(t->data);
+    for (size_t i = 0; i < n; ++i) {
+      uint32_t u = (uint32_t)s[i] << 16;
+      memcpy(&out[i], &u, 4);
+    }
+  } else if (t->dtype == DSM_F16) {
+    const uint16_t* s = static_cast<const uint16_t*>(t->data);
+    for (size_t i = 0; i < n; ++i) out[i] = half_to_float(s[i]);
+  } else fail(DSM_ERR_INVALID_ARG, "weight '%s': unsupported dtype %d", name.c_str(), t->dtype);
+  return out;
+}
+
+bool is_device_pointer(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- conversions / fills -------------------------------------------------------------------------
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void f16_to_bf16_kernel(const __half* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = __float2bfloat16_rn(__half2float(src[i]));
+}
+
+__nv_bfloat16* upload_bf16(Arena& arena, const std::vector<float>& host) {
+  dsm_tensor t{};
+  t.name = "<host>";
+  t.dtype = DSM_F32;
+  t.ndim = 1;
+  t.shape[0] = (int64_t)host.size();
+  t.data = host.data();
+  return upload_tensor_bf16(arena, &t, host.size(), 0);
+}
+
+__nv_bfloat16* upload_tensor_bf16(Arena& arena, const dsm_tensor* t, size_t expect_numel, cudaStream_t st) {
+  const size_t n = numel(t);
+  DSM_CHECK(n == expect_numel, DSM_ERR_SHAPE, "weight '%s' has %zu elements, expected %zu", t->name, n, expect_numel);
+  __nv_bfloat16* dst = arena.alloc<__nv_bfloat16>(n, false);
+  if (t->dtype == DSM_BF16) {
+    DSM_CUDA(cudaMemcpy(dst, t->data, n * 2, cudaMemcpyHostToDevice));
+    return dst;
+  }
+  // stage through a bounded scratch buffer and round on the device
+  const size_t chunk = std::min<size_t>(n, (size_t)32 << 20);
+  const size_t esz = t->dtype == DSM_F32 ? 4 : 2;
+  void* scratch = nullptr;
+  DSM_CUDA(cudaMalloc(&scratch, chunk * esz));
+  try {
+    for (size_t o = 0; o < n; o += chunk) {
+      const size_t c = std::min(chunk, n - o);
+      DSM_CUDA(cudaMemcpyAsync(scratch, static_cast<const char*>(t->data) + o * esz, c * esz, cudaMemcpyHostToDevice, st));
+      if (t->dtype == DSM_F32)
+        f32_to_bf16_kernel<<<1184, 256, 0, st>>>(static_cast<const float*>(scratch), dst + o, c);
+      else if (t->dtype == DSM_F16)
+        f16_to_bf16_kernel<<<1184, 256, 0, st>>>(static_cast<const __half*>(scratch), dst + o, c);
+      else fail(DSM_ERR_INVALID_ARG, "weight '%s': unsupported dtype %d", t->name, t->dtype);
+      DSM_CUDA(cudaGetLastError());
+      DSM_CUDA(cudaStreamSynchronize(st));
+    }
+  } catch (...) {
+    cudaFree(scratch);
+    throw;
+  }
+  cudaFree(scratch);
+  return dst;
+}
+
+__device__ __forceinline__ uint32_t hash_u64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return (uint32_t)x;
+}
+// uniform in [-sqrt(3), sqrt(3)): unit variance
+__device__ __forceinline__ float unit_uniform(uint64_t seed, size_t i) {
+  const uint32_t h = hash_u64(seed * 0x9e3779b97f4a7c15ULL + i);
+  return ((float)(h >> 8) * (1.f / 8388608.f) - 1.f) * 1.7320508f;
+}
+__global__ void fill_random_f32_kernel(float* dst, size_t n, float std, float mean, uint64_t seed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = mean + std * unit_uniform(seed, i);
+}
+__global__ void fill_random_bf16_kernel(__nv_bfloat16* dst, size_t n, float std, uint64_t seed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = __float2bfloat16_rn(std * unit_uniform(seed, i));
+}
+template <typename T>
+__global__ void fill_const_kernel(T* dst, size_t n, T v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = v;
+}
+static unsigned fill_grid(size_t n) { return (unsigned)std::min<size_t>(ceil_div<size_t>(n, 256), 148 * 8); }
+
+void fill_random_f32(float* dst, size_t n, float std, float mean, uint64_t seed, cudaStream_t st) {
+  if (!n) return;
+  fill_random_f32_kernel<<<fill_grid(n), 256, 0, st>>>(dst, n, std, mean, seed);
+  DSM_CUDA(cudaGetLastError());
+}
+void fill_random_bf16(__nv_bfloat16* dst, size_t n, float std, uint64_t seed, cudaStream_t st) {
+  if (!n) return;
+  fill_random_bf16_kernel<<<fill_grid(n), 256, 0, st>>>(dst, n, std, seed);
+  DSM_CUDA(cudaGetLastError());
+}
+void fill_const_f32(float* dst, size_t n, float v, cudaStream_t st) {
+  if (!n) return;
+  fill_const_kernel<float><<<fill_grid(n), 256, 0, st>>>(dst, n, v);
+  DSM_CUDA(cudaGetLastError());
+}
+void fill_u8(uint8_t* dst, size_t n, uint8_t v, cudaStream_t st) {
+  if (!n) return;
+  fill_const_kernel<uint8_t><<<fill_grid(n), 256, 0, st>>>(dst, n, v);
+  DSM_CUDA(cudaGetLastError());
+}
+void fill_u32(uint32_t* dst, size_t n, uint32_t v, cudaStream_t st) {
+  if (!n) return;
+  fill_const_kernel<uint32_t><<<fill_grid(n), 256, 0, st>>>(dst, n, v);
+  DSM_CUDA(cudaGetLastError());
+}
+
+// ---- CUDA graph -----------------------------------------------------------------------------------
+bool graphs_enabled() {
+  const char* e = getenv("DSM_NO_GRAPH");
+  return !(e && e[0] == '1');
+}
+
+GraphExec::~GraphExec() { reset(); }
+
+void GraphExec::reset() {
+  if (exec_) cudaGraphExecDestroy(exec_);
+  if (graph_) cudaGraphDestroy(graph_);
+  exec_ = nullptr;
+  graph_ = nullptr;
+  nodes_ = 0;
+}
+
+void GraphExec::capture(cudaStream_t st, const std::function<void()>& body) {
+  reset();
+  DSM_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const long long before = g_launch_count;
+  try {
+    body();
+  } catch (...) {
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(st, &g);
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    throw;
+  }
+  launches_ = g_launch_count - before;
+  g_launch_count = before;  // captured launches are counted when the graph is replayed
+  DSM_CUDA(cudaStreamEndCapture(st, &graph_));
+  DSM_CUDA(cudaGraphGetNodes(graph_, nullptr, &nodes_));
+  DSM_CUDA(cudaGraphInstantiate(&exec_, graph_, 0));
+}
+
+void GraphExec::launch(cudaStream_t st) {
+  DSM_CHECK(exec_ != nullptr, DSM_ERR_INVALID_ARG, "graph launched before capture");
+  DSM_CUDA(cudaGraphLaunch(exec_, st));
+  g_launch_count += launches_;
+}
+
+}  // namespace dsm

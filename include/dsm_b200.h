@@ -1,0 +1,211 @@
+/*
+ * dsm_b200.h -- C ABI of the B200-native batched streaming-STT hot path.
+ *
+ * This header is the drop-in boundary.  Each entry point replaces one method of the reference's Rust
+ * `moshi` crate (paths relative to /root/reference/server/rust/moshi/moshi-core/src unless noted);
+ * the citation next to each declaration names the method it stands in for.  The reference has no
+ * FFI of its own (everything below the Rust methods is candle), so a maintainer binds these with a
+ * plain `extern "C"` block -- see INTEGRATION.md for the Rust shim.
+ *
+ * Conventions
+ *   - Every function returns a dsm_status (0 = ok, < 0 = error); the message of the last error on the
+ *     calling thread is available through dsm_last_error().  Nothing aborts or throws across the ABI
+ *     (the reference returns candle::Result and bails, e.g. asr.rs:158-160).
+ *   - Handles own all device memory (weights, conv/KV state, workspaces) and one CUDA stream each.
+ *     They are thread-compatible, not thread-safe (the reference's objects are `&mut self`).
+ *   - Data pointers are plain row-major, batch-major buffers.  Unless stated otherwise a data pointer
+ *     may be host memory (pinned or pageable) or device memory; the library detects which.
+ *   - `mask` is `[B]` bytes on the HOST, 1 = stream active this step (StreamMask::new,
+ *     streaming.rs:42-47); NULL means all active.
+ *   - There is no CPU fallback: creating a handle without a CUDA device fails with DSM_ERR_CUDA.
+ */
+#ifndef DSM_B200_H
+#define DSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t dsm_status;
+enum {
+  DSM_OK = 0,
+  DSM_ERR_INVALID_ARG = -1,
+  DSM_ERR_SHAPE = -2,
+  DSM_ERR_CUDA = -3,
+  DSM_ERR_OOM = -4,
+  DSM_ERR_UNSUPPORTED = -5,
+  DSM_ERR_MISSING_WEIGHT = -6
+};
+
+enum { DSM_F32 = 0, DSM_BF16 = 1, DSM_F16 = 2, DSM_U32 = 3 };
+
+#define DSM_FRAME_SIZE 1920 /* moshi-server/src/batched_asr.rs:26 */
+
+/* One named host tensor (what candle's VarBuilder hands the reference's constructors). */
+typedef struct dsm_tensor {
+  const char* name;
+  int32_t dtype; /* DSM_F32 / DSM_BF16 / DSM_F16 */
+  int32_t ndim;
+  int64_t shape[4];
+  const void* data; /* host pointer, contiguous */
+} dsm_tensor;
+
+typedef struct dsm_weights {
+  const dsm_tensor* tensors;
+  int64_t count;
+} dsm_weights;
+
+/* mimi::Config::v0_1 (mimi.rs:32-93).  Zero-initialise then call dsm_mimi_spec_v0_1(). */
+typedef struct dsm_mimi_spec {
+  int32_t n_q;             /* quantizer_n_q; 32 for STT/TTS (batched_asr.rs:754) */
+  int32_t bins;            /* 2048 */
+  int32_t qdim;            /* 256 */
+  int32_t dim;             /* 512: seanet dimension == transformer d_model */
+  int32_t n_filters;       /* 64 */
+  int32_t ratios[4];       /* {8,6,5,4}; the encoder walks them reversed */
+  int32_t kernel_size;     /* 7 */
+  int32_t residual_kernel_size; /* 3 */
+  int32_t last_kernel_size;     /* 3 */
+  int32_t compress;        /* 2 */
+  int32_t num_heads;       /* 8 */
+  int32_t num_layers;      /* 8 */
+  int32_t dim_feedforward; /* 2048 */
+  int32_t context;         /* 250 */
+  float max_period;        /* 10000 */
+  float ln_eps;            /* 1e-5 */
+  int32_t downsample_stride; /* 2 */
+  int32_t with_encoder;    /* build encode_step state */
+  int32_t with_decoder;    /* build decode_step state */
+} dsm_mimi_spec;
+
+/* lm::Config as the STT TOMLs fill it (configs/stt/config-stt-en_fr-hf.toml:27-56). */
+typedef struct dsm_lm_spec {
+  int32_t d_model;
+  int32_t num_heads;
+  int32_t num_layers;
+  int32_t dim_feedforward;
+  int32_t context;
+  float max_period;
+  int32_t text_in_vocab_size;
+  int32_t text_out_vocab_size;
+  int32_t audio_vocab_size;
+  int32_t audio_codebooks;
+  int32_t extra_heads_num;
+  int32_t extra_heads_dim;
+  float rms_eps; /* 1e-8, batched_transformer.rs:246-248 */
+} dsm_lm_spec;
+
+typedef struct dsm_mimi dsm_mimi;
+typedef struct dsm_lm dsm_lm;
+typedef struct dsm_asr dsm_asr;
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* dsm_version(void);
+/* Copies the calling thread's last error message (NUL-terminated) into buf; returns its length. */
+size_t dsm_last_error(char* buf, size_t cap);
+/* Number of CUDA devices visible (0 when none: every create call will then fail). */
+int32_t dsm_device_count(void);
+/* Kernel launches issued by this library on the calling thread (graph replays count their kernels). */
+long long dsm_launch_count(void);
+void dsm_launch_count_reset(void);
+
+void dsm_mimi_spec_v0_1(dsm_mimi_spec* spec, int32_t n_q);            /* mimi.rs:32 Config::v0_1 */
+void dsm_lm_spec_stt_1b_en_fr(dsm_lm_spec* spec);                     /* config-stt-en_fr-hf.toml */
+void dsm_lm_spec_stt_2_6b_en(dsm_lm_spec* spec);                      /* config-stt-en-hf.toml */
+
+/* ---- Mimi ------------------------------------------------------------------------------- */
+/* Mimi::batched (mimi.rs:113-171).  Folds weight-norm (conv.rs:27-45) and derives codebook
+ * embeddings / c2 (quantization.rs:86-107) at load.  weights == NULL => seeded device-side random
+ * init (benchmarks only). */
+dsm_status dsm_mimi_create(const dsm_mimi_spec* spec, const dsm_weights* weights, int32_t device,
+                           int32_t batch_size, dsm_mimi** out);
+void dsm_mimi_destroy(dsm_mimi* h);
+/* Mimi::encode_step (mimi.rs:195-206).  pcm [B,1920] f32 -> codes [B,n_q] u32; *produced = 1 when a
+ * frame of codes was written (always, for 1920-sample steps).  Asynchronous on the handle's stream
+ * when `codes` is device memory; synchronous when it is host memory. */
+dsm_status dsm_mimi_encode_step(dsm_mimi* h, const float* pcm, const uint8_t* mask, uint32_t* codes,
+                                int32_t* produced);
+/* Mimi::decode_step (mimi.rs:217-225).  codes [B,n_q] u32 -> pcm [B,1920] f32. */
+dsm_status dsm_mimi_decode_step(dsm_mimi* h, const uint32_t* codes, const uint8_t* mask, float* pcm,
+                                int32_t* produced);
+/* Latent that the last encode_step fed to the quantiser, [B,dim] f32 (Mimi::encode_pre_quantize's
+ * streaming counterpart, mimi.rs:177-184); for parity checks. */
+dsm_status dsm_mimi_last_latent(dsm_mimi* h, float* latent);
+/* Parity taps: "seanet_out" [B,2,dim], "transformer_out" [B,2,dim], "latent" [B,dim] (encoder side,
+ * values of the last encode_step, time-major rows), "dec_emb" [B,dim] (quantiser output of the last
+ * decode_step).  out == NULL just reports *numel. */
+dsm_status dsm_mimi_debug_tensor(dsm_mimi* h, const char* name, float* out, int64_t cap, int64_t* numel);
+dsm_status dsm_mimi_reset_state(dsm_mimi* h);                          /* mimi.rs:227-234 */
+dsm_status dsm_mimi_reset_batch_idx(dsm_mimi* h, int32_t batch_idx);   /* mimi.rs:236-244 */
+dsm_status dsm_mimi_synchronize(dsm_mimi* h);
+int32_t dsm_mimi_batch_size(const dsm_mimi* h);
+int32_t dsm_mimi_n_q(const dsm_mimi* h);
+int64_t dsm_mimi_device_bytes(const dsm_mimi* h);
+int64_t dsm_mimi_kv_bytes(const dsm_mimi* h);
+
+/* ---- LM --------------------------------------------------------------------------------- */
+/* LmModel::batched (lm.rs:812-897), depformer-less (STT).  Weights are rounded to bf16 on load
+ * (model_dtype == bf16 on CUDA, moshi-server/src/utils.rs:386-395). */
+dsm_status dsm_lm_create(const dsm_lm_spec* spec, const dsm_weights* weights, int32_t device,
+                         int32_t batch_size, dsm_lm** out);
+void dsm_lm_destroy(dsm_lm* h);
+/* LmModel::forward_cond (lm.rs:957-1008): text_ids [B] u32, audio_ids [B,n_cb] u32,
+ * cond [d_model] f32 or NULL (Condition::AddToInput) -> logits [B,V] f32 and ys [B,D] f32 (either
+ * may be NULL).  The reference returns bf16 tensors; f32 here is the same values widened. */
+dsm_status dsm_lm_forward(dsm_lm* h, const uint32_t* text_ids, const uint32_t* audio_ids,
+                          const float* cond, const uint8_t* mask, float* logits, float* ys);
+dsm_status dsm_lm_reset_state(dsm_lm* h);                              /* lm.rs:899-902 */
+dsm_status dsm_lm_reset_batch_idx(dsm_lm* h, int32_t batch_idx);       /* lm.rs:1108-1110 */
+dsm_status dsm_lm_synchronize(dsm_lm* h);
+int32_t dsm_lm_text_start_token(const dsm_lm* h);                      /* lm.rs:916-918 */
+int32_t dsm_lm_audio_pad_token(const dsm_lm* h);                       /* lm.rs:912-914 */
+int32_t dsm_lm_in_audio_codebooks(const dsm_lm* h);                    /* lm.rs:904-906 */
+/* Bytes of device memory the handle's ring KV cache occupies (for the roofline arithmetic). */
+int64_t dsm_lm_kv_bytes(const dsm_lm* h);
+int64_t dsm_lm_weight_bytes(const dsm_lm* h);
+
+/* ---- ASR state -------------------------------------------------------------------------- */
+/* asr::AsrMsg (asr.rs:9-13). */
+enum { DSM_MSG_STEP = 0, DSM_MSG_WORD = 1, DSM_MSG_END_WORD = 2 };
+typedef struct dsm_asr_msg {
+  int32_t kind;
+  int32_t batch_idx;      /* WORD / END_WORD */
+  int32_t step_idx;       /* STEP: model_step_idx after the step */
+  int32_t n_tokens;       /* WORD */
+  const uint32_t* tokens; /* WORD: valid until the next step call on this handle */
+  double time;            /* WORD: start_time, END_WORD: stop_time (seconds) */
+  const float* prs;       /* STEP: [n_heads * B], prs[h*B + b]; valid until the next step */
+} dsm_asr_msg;
+
+/* asr::State::new (asr.rs:64-88).  Borrows mimi and lm (they must outlive the state; mimi may be
+ * NULL when only step_tokens is used).  temperature must be <= 0 (greedy, asr.rs:208-210). */
+dsm_status dsm_asr_create(dsm_mimi* mimi, dsm_lm* lm, int32_t asr_delay_in_tokens, float temperature,
+                          dsm_asr** out);
+void dsm_asr_destroy(dsm_asr* h);
+/* asr::State::step_pcm (asr.rs:115-131): Mimi encode of this frame runs concurrently with the LM
+ * step on the previous frame's codes (asr.rs:172-183).  text_tokens [B] u32 HOST out (may be NULL).
+ * Messages of the step are read with dsm_asr_msg_count / dsm_asr_msg_get. */
+dsm_status dsm_asr_step_pcm(dsm_asr* h, const float* pcm, const uint8_t* mask, uint32_t* text_tokens);
+/* asr::State::step_tokens / step_tokens_vec (asr.rs:147-255, 268-283): codes [B,n_cb] u32. */
+dsm_status dsm_asr_step_tokens(dsm_asr* h, const uint32_t* codes, const uint8_t* mask,
+                               uint32_t* text_tokens);
+int32_t dsm_asr_msg_count(const dsm_asr* h);
+dsm_status dsm_asr_msg_get(const dsm_asr* h, int32_t i, dsm_asr_msg* out);
+dsm_status dsm_asr_reset(dsm_asr* h);                                  /* asr.rs:104-113 */
+dsm_status dsm_asr_reset_batch_idx(dsm_asr* h, int32_t batch_idx);     /* asr.rs:257-266 */
+int32_t dsm_asr_batch_size(const dsm_asr* h);                          /* asr.rs:94-96 */
+int32_t dsm_asr_model_step_idx(const dsm_asr* h);                      /* asr.rs:90-92 */
+int32_t dsm_asr_delay_in_tokens(const dsm_asr* h);                     /* asr.rs:98-100 */
+/* Text logits [B,V] f32 of the last step (what asr.rs:208-210 takes the argmax of); parity only. */
+dsm_status dsm_asr_last_logits(dsm_asr* h, float* logits);
+/* Device-side timing of the last step (ms) measured with CUDA events on the handle's streams:
+ * out[0] = whole step, out[1] = Mimi encode branch, out[2] = LM branch. */
+dsm_status dsm_asr_last_step_ms(dsm_asr* h, float out[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSM_B200_H */

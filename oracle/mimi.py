@@ -262,7 +262,9 @@ class Mimi:
         """encode_step up to (excluding) the quantiser: ``[B, 1, 1920]`` -> ``[B, 512, 1]``."""
         cpu_mask, tmask = self._mask(mask, pcm.shape[0])
         xs = self.encoder.step(pcm, tmask)
+        self._last_seanet = None if xs is None else xs.transpose(1, 2).numpy().copy()
         xs = self.encoder_transformer.step(xs, cpu_mask)
+        self._last_transformer = None if xs is None else xs.transpose(1, 2).numpy().copy()
         return self.downsample.step(xs, tmask)
 
     def encode_step(self, pcm: torch.Tensor, mask=None) -> Optional[torch.Tensor]:
@@ -270,6 +272,7 @@ class Mimi:
         xs = self.encode_latent_step(pcm, mask)
         if xs is None:
             return None
+        self._last_latent = xs[:, :, 0].numpy().copy()
         return self.quantizer.encode(xs)
 
     def decode_step(self, codes: torch.Tensor, mask=None) -> Optional[torch.Tensor]:
