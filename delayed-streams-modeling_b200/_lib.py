@@ -65,8 +65,10 @@ SIGNATURES = {
     "dsm_version": (C.c_char_p, []),
     "dsm_last_error": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "dsm_device_count": (C.c_int32, []),
+    "dsm_set_graphs": (None, [C.c_int32]),
     "dsm_launch_count": (C.c_longlong, []),
     "dsm_launch_count_reset": (None, []),
+    "dsm_debug_gemm_bf16": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "dsm_mimi_spec_v0_1": (None, [C.POINTER(MimiSpecC), C.c_int32]),
     "dsm_lm_spec_stt_1b_en_fr": (None, [C.POINTER(LmSpecC)]),
     "dsm_lm_spec_stt_2_6b_en": (None, [C.POINTER(LmSpecC)]),
@@ -92,6 +94,11 @@ SIGNATURES = {
     "dsm_lm_text_start_token": (C.c_int32, [_P]),
     "dsm_lm_audio_pad_token": (C.c_int32, [_P]),
     "dsm_lm_in_audio_codebooks": (C.c_int32, [_P]),
+    "dsm_lm_stream": (C.c_void_p, [_P]),
+    "dsm_mimi_stream": (C.c_void_p, [_P]),
+    "dsm_lm_profile_attention": (C.c_int32, [_P, C.c_int32]),
+    "dsm_lm_profile_read": (C.c_int32, [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "dsm_lm_debug_set_position": (C.c_int32, [_P, C.c_uint32]),
     "dsm_lm_kv_bytes": (C.c_int64, [_P]),
     "dsm_lm_weight_bytes": (C.c_int64, [_P]),
     "dsm_asr_create": (C.c_int32, [_P, _P, C.c_int32, C.c_float, C.POINTER(_P)]),

@@ -179,6 +179,21 @@ class LmModel:
     def in_audio_codebooks(self) -> int:
         return self._lib.dsm_lm_in_audio_codebooks(self._h)
 
+    def stream(self) -> int:
+        """Raw cudaStream_t of the handle (wrap with torch.cuda.ExternalStream to record events on it)."""
+        return self._lib.dsm_lm_stream(self._h)
+
+    def debug_set_position(self, pos: int):
+        check(self._lib.dsm_lm_debug_set_position(self._h, pos))
+
+    def profile_attention(self, enable: bool):
+        check(self._lib.dsm_lm_profile_attention(self._h, int(enable)))
+
+    def profile_read(self) -> Tuple[float, int]:
+        ms, n = C.c_double(0), C.c_longlong(0)
+        check(self._lib.dsm_lm_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     @property
     def kv_bytes(self) -> int:
         return self._lib.dsm_lm_kv_bytes(self._h)
@@ -271,6 +286,10 @@ class AsrState:
 
     def reset_batch_idx(self, batch_idx: int):
         check(self._lib.dsm_asr_reset_batch_idx(self._h, batch_idx))
+
+
+def set_graphs(enabled: bool):
+    _lib.load().dsm_set_graphs(int(enabled))
 
 
 def launch_count() -> int:

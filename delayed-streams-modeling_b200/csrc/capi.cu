@@ -55,6 +55,7 @@ int32_t dsm_device_count(void) {
   return n;
 }
 
+void dsm_set_graphs(int32_t enabled) { set_graphs_enabled(enabled); }
 long long dsm_launch_count(void) { return g_launch_count; }
 void dsm_launch_count_reset(void) { g_launch_count = 0; }
 
@@ -100,6 +101,49 @@ static void require_device(int32_t device) {
   DSM_CUDA(cudaGetDeviceProperties(&p, device));
   DSM_CHECK(p.major == 10, DSM_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
             p.major, p.minor);
+}
+
+// Stand-alone GEMM check: out = X[M,K] . W[N,K]^T (bf16 bit patterns in, f32 accumulate) through the
+// CUDA-core kernel (impl 0) or the tcgen05 kernel (impl 1).  mode: 0 store f32 [M,N]; 1 accumulate into
+// inout_f32 [M,N]; 2 gated pair -> out_bf16 [M, N/2] = silu(acc[:, j]) * acc[:, N/2 + j].
+dsm_status dsm_debug_gemm_bf16(int32_t impl, int32_t mode, int32_t M, int32_t N, int32_t K, const uint16_t* X,
+                               const uint16_t* W, float* inout_f32, uint16_t* out_bf16) {
+  return guarded([&] {
+    REQUIRE(X && W, "X and W are required");
+    require_device(0);
+    DSM_CUDA(cudaSetDevice(0));
+    Arena a;
+    __nv_bfloat16* dX = a.alloc<__nv_bfloat16>((size_t)M * K);
+    __nv_bfloat16* dW = a.alloc<__nv_bfloat16>((size_t)N * K);
+    float* dO = a.alloc<float>((size_t)M * N);
+    __nv_bfloat16* dG = a.alloc<__nv_bfloat16>((size_t)M * (N / 2 + 1));
+    DSM_CUDA(cudaMemcpy(dX, X, (size_t)M * K * 2, cudaMemcpyHostToDevice));
+    DSM_CUDA(cudaMemcpy(dW, W, (size_t)N * K * 2, cudaMemcpyHostToDevice));
+    if (mode == 1) {
+      REQUIRE(inout_f32, "inout_f32 is required");
+      DSM_CUDA(cudaMemcpy(dO, inout_f32, (size_t)M * N * 4, cudaMemcpyHostToDevice));
+    }
+    if (impl == 1) {
+      TcGemm g;
+      tc_gemm_prepare(g, dW, dX, M, N, K, mode, dO, dG);
+      tc_gemm_launch(g, 0);
+    } else {
+      GemmParams g;
+      g.A = dX, g.a_map = dense_rows(1, K), g.W = dW, g.M = M, g.N = N, g.K = K;
+      g.out_raw = dO, g.o_map = dense_rows(1, N);
+      if (mode == 1) g.res = dO, g.r_map = dense_rows(1, N);
+      launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(g, 0);
+      if (mode == 2) launch_silu_gate(dO, M, N / 2, dG, 0);
+    }
+    DSM_CUDA(cudaDeviceSynchronize());
+    if (mode == 2) {
+      REQUIRE(out_bf16, "out_bf16 is required");
+      DSM_CUDA(cudaMemcpy(out_bf16, dG, (size_t)M * (N / 2) * 2, cudaMemcpyDeviceToHost));
+    } else {
+      REQUIRE(inout_f32, "inout_f32 is required");
+      DSM_CUDA(cudaMemcpy(inout_f32, dO, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+    }
+  });
 }
 
 // ---- Mimi ----------------------------------------------------------------------------------------
@@ -236,6 +280,31 @@ dsm_status dsm_lm_synchronize(dsm_lm* h) {
 int32_t dsm_lm_text_start_token(const dsm_lm* h) { return h ? h->impl->spec.text_in_vocab_size - 1 : -1; }
 int32_t dsm_lm_audio_pad_token(const dsm_lm* h) { return h ? h->impl->spec.audio_vocab_size - 1 : -1; }
 int32_t dsm_lm_in_audio_codebooks(const dsm_lm* h) { return h ? h->impl->spec.audio_codebooks : 0; }
+void* dsm_lm_stream(const dsm_lm* h) { return h ? (void*)h->impl->stream : nullptr; }
+void* dsm_mimi_stream(const dsm_mimi* h) { return h ? (void*)h->impl->stream : nullptr; }
+dsm_status dsm_lm_profile_attention(dsm_lm* h, int32_t enable) {
+  return guarded([&] {
+    REQUIRE(h, "handle is required");
+    h->impl->profile_attn = enable != 0;
+    h->impl->prof_used = 0;
+  });
+}
+dsm_status dsm_lm_profile_read(dsm_lm* h, double* ms_sum, long long* launches) {
+  return guarded([&] {
+    REQUIRE(h, "handle is required");
+    h->impl->profile_read(ms_sum, launches);
+  });
+}
+dsm_status dsm_lm_debug_set_position(dsm_lm* h, uint32_t pos) {
+  return guarded([&] {
+    REQUIRE(h, "handle is required");
+    LmImpl* l = h->impl;
+    DSM_CUDA(cudaSetDevice(l->device));
+    fill_u32(l->ring.positions, l->B, pos, l->stream);
+    fill_u32(l->ring.indices, l->B, pos % (uint32_t)l->ctx, l->stream);
+    DSM_CUDA(cudaStreamSynchronize(l->stream));
+  });
+}
 int64_t dsm_lm_kv_bytes(const dsm_lm* h) { return h ? (int64_t)h->impl->kv_bytes : 0; }
 int64_t dsm_lm_weight_bytes(const dsm_lm* h) { return h ? (int64_t)h->impl->weight_bytes : 0; }
 

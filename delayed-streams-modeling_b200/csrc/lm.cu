@@ -135,6 +135,20 @@ LmImpl::LmImpl(const dsm_lm_spec& sp, const dsm_weights* w, int dev, int batch) 
   ys_f32 = arena.alloc<float>((size_t)B * D);
   logits = arena.alloc<float>((size_t)B * sp.text_out_vocab_size);
 
+  {
+    const char* e = getenv("DSM_LM_GEMM");
+    use_tc = !(e && std::string(e) == "simt");
+  }
+  if (use_tc) {
+    for (int l = 0; l < L; ++l) {
+      Layer& y = layers[l];
+      tc_gemm_prepare(y.g_qkv, y.in_proj, xn, B, 3 * D, D, TC_STORE_F32, qkv, nullptr);
+      tc_gemm_prepare(y.g_out, y.out_proj, attn, B, D, D, TC_ACCUM_F32, x, nullptr);
+      tc_gemm_prepare(y.g_in, y.lin_in, xn, B, 2 * hidden, D, TC_GATE_BF16, nullptr, gbuf);
+      tc_gemm_prepare(y.g_down, y.lin_out, gbuf, B, D, hidden, TC_ACCUM_F32, x, nullptr);
+    }
+    tc_gemm_prepare(g_text, text_linear, ys_bf16, B, sp.text_out_vocab_size, D, TC_STORE_F32, logits, nullptr);
+  }
   build_plan(plan, false);
   build_plan(plan_cond, true);
   DSM_CUDA(cudaStreamSynchronize(stream));
@@ -145,6 +159,10 @@ LmImpl::~LmImpl() {
   if (stream) cudaStreamSynchronize(stream);
   graph.reset();
   graph_cond.reset();
+  for (auto& e : prof_events) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -161,36 +179,89 @@ void LmImpl::build_plan(Plan& p, bool with_cond) {
     p.push_back([=](cudaStream_t st) {
       const int B = s->B, D = s->D, Hd = s->hidden;
       launch_rmsnorm(s->x, y.norm1, s->spec.rms_eps, B, D, s->xn, nullptr, st);
-      GemmParams g;
-      g.A = s->xn, g.a_map = dense_rows(1, D), g.W = y.in_proj, g.M = B, g.N = 3 * D, g.K = D;
-      g.out_raw = s->qkv, g.o_map = dense_rows(1, 3 * D);
-      launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(g, st);
+      if (s->use_tc) {
+        tc_gemm_launch(y.g_qkv, st);
+      } else {
+        GemmParams g;
+        g.A = s->xn, g.a_map = dense_rows(1, D), g.W = y.in_proj, g.M = B, g.N = 3 * D, g.K = D;
+        g.out_raw = s->qkv, g.o_map = dense_rows(1, 3 * D);
+        launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(g, st);
+      }
       launch_rope_scatter_bf16(s->qkv, s->ring, B, s->H, s->hd, s->ctx, s->inv_freq, s->q, y.k_ring, y.v_ring, st);
+      s->profile_begin(st);
       launch_lm_attention(s->q, s->ring, s->d_mask, B, s->H, s->hd, s->ctx, y.k_ring, y.v_ring, s->attn, st);
-      GemmParams o;   // x += out_proj(attn)
-      o.A = s->attn, o.a_map = dense_rows(1, D), o.W = y.out_proj, o.M = B, o.N = D, o.K = D;
-      o.res = s->x, o.r_map = dense_rows(1, D), o.out_raw = s->x, o.o_map = dense_rows(1, D);
-      launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(o, st);
+      s->profile_end(st);
+      if (s->use_tc) {
+        tc_gemm_launch(y.g_out, st);       // x += out_proj(attn)
+      } else {
+        GemmParams o;
+        o.A = s->attn, o.a_map = dense_rows(1, D), o.W = y.out_proj, o.M = B, o.N = D, o.K = D;
+        o.res = s->x, o.r_map = dense_rows(1, D), o.out_raw = s->x, o.o_map = dense_rows(1, D);
+        launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(o, st);
+      }
       launch_rmsnorm(s->x, y.norm2, s->spec.rms_eps, B, D, s->xn, nullptr, st);
-      GemmParams f1;
-      f1.A = s->xn, f1.a_map = dense_rows(1, D), f1.W = y.lin_in, f1.M = B, f1.N = 2 * Hd, f1.K = D;
-      f1.out_raw = s->hbuf, f1.o_map = dense_rows(1, 2 * Hd);
-      launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(f1, st);
-      launch_silu_gate(s->hbuf, B, Hd, s->gbuf, st);
-      GemmParams f2;  // x += linear_out(silu(gate) * value)
-      f2.A = s->gbuf, f2.a_map = dense_rows(1, Hd), f2.W = y.lin_out, f2.M = B, f2.N = D, f2.K = Hd;
-      f2.res = s->x, f2.r_map = dense_rows(1, D), f2.out_raw = s->x, f2.o_map = dense_rows(1, D);
-      launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(f2, st);
+      if (s->use_tc) {
+        tc_gemm_launch(y.g_in, st);        // gbuf = silu(gate) * value
+        tc_gemm_launch(y.g_down, st);      // x += linear_out(gbuf)
+      } else {
+        GemmParams f1;
+        f1.A = s->xn, f1.a_map = dense_rows(1, D), f1.W = y.lin_in, f1.M = B, f1.N = 2 * Hd, f1.K = D;
+        f1.out_raw = s->hbuf, f1.o_map = dense_rows(1, 2 * Hd);
+        launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(f1, st);
+        launch_silu_gate(s->hbuf, B, Hd, s->gbuf, st);
+        GemmParams f2;
+        f2.A = s->gbuf, f2.a_map = dense_rows(1, Hd), f2.W = y.lin_out, f2.M = B, f2.N = D, f2.K = Hd;
+        f2.res = s->x, f2.r_map = dense_rows(1, D), f2.out_raw = s->x, f2.o_map = dense_rows(1, D);
+        launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(f2, st);
+      }
     });
   }
   p.push_back([=](cudaStream_t st) {
     const int B = s->B, D = s->D, V = s->spec.text_out_vocab_size;
     launch_rmsnorm(s->x, s->out_norm, s->spec.rms_eps, B, D, s->ys_bf16, s->ys_f32, st);
-    GemmParams g;
-    g.A = s->ys_bf16, g.a_map = dense_rows(1, D), g.W = s->text_linear, g.M = B, g.N = V, g.K = D;
-    g.out_raw = s->logits, g.o_map = dense_rows(1, V);
-    launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(g, st);
+    if (s->use_tc) {
+      tc_gemm_launch(s->g_text, st);
+    } else {
+      GemmParams g;
+      g.A = s->ys_bf16, g.a_map = dense_rows(1, D), g.W = s->text_linear, g.M = B, g.N = V, g.K = D;
+      g.out_raw = s->logits, g.o_map = dense_rows(1, V);
+      launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(g, st);
+    }
   });
+}
+
+static bool stream_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  return cs != cudaStreamCaptureStatusNone;
+}
+void LmImpl::profile_begin(cudaStream_t st) {
+  if (!profile_attn || stream_capturing(st)) return;
+  if (prof_used == prof_events.size()) {
+    cudaEvent_t a, b;
+    DSM_CUDA(cudaEventCreate(&a));
+    DSM_CUDA(cudaEventCreate(&b));
+    prof_events.emplace_back(a, b);
+  }
+  DSM_CUDA(cudaEventRecord(prof_events[prof_used].first, st));
+}
+void LmImpl::profile_end(cudaStream_t st) {
+  if (!profile_attn || stream_capturing(st)) return;
+  DSM_CUDA(cudaEventRecord(prof_events[prof_used].second, st));
+  ++prof_used;
+}
+void LmImpl::profile_read(double* ms_sum, long long* launches) {
+  DSM_CUDA(cudaSetDevice(device));
+  DSM_CUDA(cudaStreamSynchronize(stream));
+  double tot = 0.0;
+  for (size_t i = 0; i < prof_used; ++i) {
+    float ms = 0.f;
+    DSM_CUDA(cudaEventElapsedTime(&ms, prof_events[i].first, prof_events[i].second));
+    tot += ms;
+  }
+  if (ms_sum) *ms_sum = tot;
+  if (launches) *launches = (long long)prof_used;
+  prof_used = 0;
 }
 
 void LmImpl::upload_mask(const uint8_t* host_mask, cudaStream_t st) {

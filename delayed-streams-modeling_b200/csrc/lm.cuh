@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "runtime.cuh"
 
@@ -30,7 +31,10 @@ struct LmImpl {
     __nv_bfloat16 *in_proj, *out_proj, *lin_in, *lin_out;
     float *norm1, *norm2;
     __nv_bfloat16 *k_ring, *v_ring;     // [B, H, ctx, hd]
+    TcGemm g_qkv, g_out, g_in, g_down;  // tcgen05 GEMM descriptors (tensor maps over the buffers below)
   };
+  TcGemm g_text;
+  bool use_tc = true;                   // DSM_LM_GEMM=simt selects the CUDA-core GEMM (A/B debugging)
   std::vector<Layer> layers;
   float* out_norm = nullptr;
   __nv_bfloat16* text_linear = nullptr; // [V, D]
@@ -52,6 +56,14 @@ struct LmImpl {
   __nv_bfloat16* ys_bf16 = nullptr;     // [B, D]
   float* ys_f32 = nullptr;              // [B, D]
   float* logits = nullptr;              // [B, V]
+
+  // optional per-launch timing of the attention kernel (bench.py's roofline leg; eager mode only)
+  bool profile_attn = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
+  void profile_begin(cudaStream_t st);
+  void profile_end(cudaStream_t st);
+  void profile_read(double* ms_sum, long long* launches);
 
   Plan plan;        // forward without conditioning
   Plan plan_cond;   // forward with Condition::AddToInput

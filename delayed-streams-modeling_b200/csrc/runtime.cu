@@ -219,7 +219,10 @@ void fill_u32(uint32_t* dst, size_t n, uint32_t v, cudaStream_t st) {
 }
 
 // ---- CUDA graph -----------------------------------------------------------------------------------
+static int g_graphs_override = -1;   // -1: follow DSM_NO_GRAPH, 0/1: forced by dsm_set_graphs
+void set_graphs_enabled(int v) { g_graphs_override = v; }
 bool graphs_enabled() {
+  if (g_graphs_override >= 0) return g_graphs_override != 0;
   const char* e = getenv("DSM_NO_GRAPH");
   return !(e && e[0] == '1');
 }

@@ -86,7 +86,8 @@ class GraphExec {
   long long launches_ = 0;  // kernel launches inside one replay
 };
 
-bool graphs_enabled();  // false when DSM_NO_GRAPH=1
+bool graphs_enabled();  // false when DSM_NO_GRAPH=1 or dsm_set_graphs(0)
+void set_graphs_enabled(int v);
 const std::string& last_error();
 
 }  // namespace dsm

@@ -109,8 +109,18 @@ size_t dsm_last_error(char* buf, size_t cap);
 /* Number of CUDA devices visible (0 when none: every create call will then fail). */
 int32_t dsm_device_count(void);
 /* Kernel launches issued by this library on the calling thread (graph replays count their kernels). */
+/* 1 (default): steps replay a captured CUDA graph; 0: eager launches (debugging / per-kernel timing).
+ * The environment variable DSM_NO_GRAPH=1 has the same effect as dsm_set_graphs(0). */
+void dsm_set_graphs(int32_t enabled);
 long long dsm_launch_count(void);
 void dsm_launch_count_reset(void);
+
+/* Stand-alone check of the projection GEMM kernels on device 0: out = X[M,K] . W[N,K]^T with bf16 bit
+ * patterns in and f32 accumulation, through the CUDA-core kernel (impl 0) or the tcgen05 kernel
+ * (impl 1).  mode 0: store f32 [M,N]; 1: accumulate into inout_f32 [M,N]; 2: gated pair ->
+ * out_bf16 [M,N/2] = silu(acc[:, j]) * acc[:, N/2 + j] (batched_transformer.rs:170-176). */
+dsm_status dsm_debug_gemm_bf16(int32_t impl, int32_t mode, int32_t M, int32_t N, int32_t K, const uint16_t* X,
+                               const uint16_t* W, float* inout_f32, uint16_t* out_bf16);
 
 void dsm_mimi_spec_v0_1(dsm_mimi_spec* spec, int32_t n_q);            /* mimi.rs:32 Config::v0_1 */
 void dsm_lm_spec_stt_1b_en_fr(dsm_lm_spec* spec);                     /* config-stt-en_fr-hf.toml */
@@ -164,6 +174,16 @@ int32_t dsm_lm_text_start_token(const dsm_lm* h);                      /* lm.rs:
 int32_t dsm_lm_audio_pad_token(const dsm_lm* h);                       /* lm.rs:912-914 */
 int32_t dsm_lm_in_audio_codebooks(const dsm_lm* h);                    /* lm.rs:904-906 */
 /* Bytes of device memory the handle's ring KV cache occupies (for the roofline arithmetic). */
+/* The handle's cudaStream_t (for recording caller-side CUDA events around steps). */
+void* dsm_lm_stream(const dsm_lm* h);
+void* dsm_mimi_stream(const dsm_mimi* h);
+/* Per-launch CUDA-event timing of the ring-attention kernel (eager mode only; measurement aid):
+ * enable, run steps, then read the summed kernel time and the number of launches timed. */
+dsm_status dsm_lm_profile_attention(dsm_lm* h, int32_t enable);
+dsm_status dsm_lm_profile_read(dsm_lm* h, double* ms_sum, long long* launches);
+/* Profiling aid: pretend every stream has already consumed `pos` frames (ring contents are left as
+ * they are), so a short profiled run reads full rings without replaying `context` steps first. */
+dsm_status dsm_lm_debug_set_position(dsm_lm* h, uint32_t pos);
 int64_t dsm_lm_kv_bytes(const dsm_lm* h);
 int64_t dsm_lm_weight_bytes(const dsm_lm* h);
 
