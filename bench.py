@@ -46,6 +46,27 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def stream_range(rank: int, streams_per_gpu: int):
+    """Streams [first, last) owned by `rank`: a disjoint slice per GPU, no step-path exchange."""
+    return rank * streams_per_gpu, (rank + 1) * streams_per_gpu
+
+
+def max_over_ranks(ms: float, world: int, device="cpu") -> float:
+    """The job finishes when its slowest rank does: MAX-reduce of the device-timed duration."""
+    if world <= 1:
+        return float(ms)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def job_throughput(world: int, streams_per_gpu: int, steps: int, ms_max: float) -> float:
+    """Whole-job stream-frames/s: every rank processed streams_per_gpu * steps frames in ms_max."""
+    return world * streams_per_gpu * steps / (ms_max * 1e-3)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -213,7 +234,7 @@ def run_ours(args):
 
     # synthetic audio: a few distinct frames per stream, cycled (content does not change the work done)
     n_audio = 8
-    audio = synth_audio(B, n_audio, first_stream=rank * B)
+    audio = synth_audio(B, n_audio, first_stream=stream_range(rank, B)[0])
     dev_frames = [torch.from_numpy(frame(audio, i)).cuda() for i in range(n_audio)]
     host_frames = [torch.from_numpy(frame(audio, i)).pin_memory() for i in range(n_audio)]
     codes_dev = torch.empty((B, mspec.n_q), dtype=torch.int32, device="cuda")
@@ -232,10 +253,7 @@ def run_ours(args):
             step(i, src)
         e1.record(ext)
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return max_over_ranks(e0.elapsed_time(e1), world, "cuda")
 
     # fill and wrap every ring (LM 750 slots, codec 250) before any timing
     for i in range(args.prefill):
@@ -251,9 +269,8 @@ def run_ours(args):
     ms_e2e = timed(args.steps, host_frames)
     clocks = sampler.stop() if rank == 0 else None
 
-    total_frames = world * B * args.steps
-    value = total_frames / (ms_dev * 1e-3)
-    e2e = total_frames / (ms_e2e * 1e-3)
+    value = job_throughput(world, B, args.steps, ms_dev)
+    e2e = job_throughput(world, B, args.steps, ms_e2e)
 
     # ---- roofline of the dominant kernel: single-query ring attention (LM), timed per launch ----
     roofline = None
