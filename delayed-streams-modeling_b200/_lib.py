@@ -69,6 +69,8 @@ SIGNATURES = {
     "dsm_launch_count": (C.c_longlong, []),
     "dsm_launch_count_reset": (None, []),
     "dsm_debug_gemm_bf16": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "dsm_debug_gemm_f32": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P,
+                                       C.c_int64, _P, _P, _P]),
     "dsm_mimi_spec_v0_1": (None, [C.POINTER(MimiSpecC), C.c_int32]),
     "dsm_lm_spec_stt_1b_en_fr": (None, [C.POINTER(LmSpecC)]),
     "dsm_lm_spec_stt_2_6b_en": (None, [C.POINTER(LmSpecC)]),

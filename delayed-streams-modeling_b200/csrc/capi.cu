@@ -146,6 +146,38 @@ dsm_status dsm_debug_gemm_bf16(int32_t impl, int32_t mode, int32_t M, int32_t N,
   });
 }
 
+// Stand-alone check of the codec GEMM kernels: out[(b,t), n] = sum_k A[b*stride_b + t*stride_t + k] * W[n, k]
+// (the implicit-GEMM conv window form), f32 in / f32 out, through the CUDA-core kernel (impl 0) or the
+// tcgen05 split-bf16 kernel (impl 1).
+dsm_status dsm_debug_gemm_f32(int32_t impl, int32_t B, int32_t T, int64_t stride_b, int64_t stride_t, int32_t N, int32_t K,
+                              const float* A, int64_t a_elems, const float* W, const float* bias, float* out) {
+  return guarded([&] {
+    REQUIRE(A && W && out, "A, W and out are required");
+    require_device(0);
+    DSM_CUDA(cudaSetDevice(0));
+    Arena a;
+    float* dA = a.alloc<float>((size_t)a_elems);
+    float* dO = a.alloc<float>((size_t)B * T * N);
+    DSM_CUDA(cudaMemcpy(dA, A, (size_t)a_elems * 4, cudaMemcpyHostToDevice));
+    std::vector<float> hw(W, W + (size_t)N * K);
+    GemmParams g;
+    g.A = dA, g.a_map = RowMap{T, (long long)stride_b, (long long)stride_t}, g.M = B * T, g.N = N, g.K = K;
+    g.out_raw = dO, g.o_map = dense_rows(1, N);
+    if (bias) g.bias = a.upload(std::vector<float>(bias, bias + N));
+    if (impl == 1) {
+      DSM_CHECK(tc6_supported(g), DSM_ERR_UNSUPPORTED, "shape not supported by the tensor-core codec GEMM");
+      Tc6Gemm t;
+      tc6_prepare(t, g, tc6_split_weights(a, hw, N, K));
+      tc6_launch(t, 0);
+    } else {
+      g.W = a.upload(hw);
+      launch_gemm_simt<float, float>(g, 0);
+    }
+    DSM_CUDA(cudaDeviceSynchronize());
+    DSM_CUDA(cudaMemcpy(out, dO, (size_t)B * T * N * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
 // ---- Mimi ----------------------------------------------------------------------------------------
 dsm_status dsm_mimi_create(const dsm_mimi_spec* spec, const dsm_weights* weights, int32_t device, int32_t batch_size,
                            dsm_mimi** out) {

@@ -1,0 +1,518 @@
+// f32-accurate GEMM on the tcgen05 tensor pipe for the Mimi codec:  C[m, n] = sum_k A[m, k] * W[n, k],
+// A and C in f32, by splitting every f32 operand into three bf16 terms (8 + 8 + 8 mantissa bits) and
+// issuing the six significant cross products  a1w1 + a1w2 + a2w1 + a1w3 + a2w2 + a3w1  as kind::f16 MMAs
+// that accumulate in f32 in TMEM.  The dropped terms are <= 2^-24 relative, so RVQ codes stay
+// bit-identical to the f32 reference (TF32 or single-bf16 tiles flip ~1/3 of frames) while the work moves
+// from the CUDA cores (~45 TFLOP/s achieved) to the tensor pipe (2.25 PFLOP/s / 6).
+//
+//   warp 0 lane 0 : TMA of the f32 A tile (implicit-GEMM conv window: a 3-D box over [B, T_out, k*C_in]
+//                   with overlapping row stride) into a 128B-swizzled staging buffer
+//   warp 3 lane 0 : TMA of the pre-split bf16 W planes (ring of stages)
+//   warps 4-11    : converters -- read staging, split f32 -> 3 x bf16, write the three K-major 128B-
+//                   swizzled UMMA operand tiles, fence.proxy.async, signal the MMA warp
+//   warp 1 lane 0 : tcgen05.mma issuer: per k-block, for each of NJ column sub-tiles, 6 x 4 MMAs
+//   warp 2        : TMEM alloc / dealloc
+//   all 12 warps  : epilogue (tcgen05.ld -> bias / c2-dot / GELU / LayerScale / residual / ELU copy)
+#include "gemm_tc6.cuh"
+
+#include <mutex>
+
+namespace dsm {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// K-major SWIZZLE_128B tile with 128-byte rows (see gemm_tc.cu)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// x = b1 + b2 + b3 (+ <= 2^-24 |x|), each term a bf16
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& b1, __nv_bfloat16& b2, __nv_bfloat16& b3) {
+  b1 = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(b1);
+  b2 = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(b2);
+  b3 = __float2bfloat16_rn(r2);
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+  return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
+
+constexpr int T6_BM = 128;           // rows per CTA (UMMA M)
+constexpr int T6_BK = 64;            // K elements per k-block
+constexpr int T6_STG_SUB = T6_BM * 32 * 4;       // one staging sub-tile: 128 rows x 32 f32 (128-byte rows)
+constexpr int T6_STG = 2 * T6_STG_SUB;           // 32 KB per k-block
+constexpr int T6_PLANE = T6_BM * T6_BK * 2;      // 16 KB per bf16 plane tile
+constexpr int T6_THREADS = 384;
+
+}  // namespace
+
+struct Tc6Params {
+  int K, N;            // N = total output columns
+  int T_out, B;        // logical rows = B * T_out, row m = b * T_out + t
+  int t_sub, b_sub;    // rows of one tile = t_sub * b_sub (<= 128)
+  int t_tiles;         // ceil(T_out / t_sub)
+  int nj;              // column sub-tiles per CTA
+  int pm;              // main-term accumulators the k-blocks rotate over (see the MMA issuer)
+  const float* bias;
+  int neg;
+  const float* scale;
+  const float* res;
+  RowMap r_map;
+  int act;
+  float* out_raw;
+  RowMap o_map;
+  float* out_act;
+  RowMap e_map;
+};
+
+template <int BN, int WS>
+__global__ void __launch_bounds__(T6_THREADS, 1)
+tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Tc6Params p) {
+  constexpr int W_STAGE = 3 * BN * T6_BK * 2;   // three bf16 planes of a BN x 64 tile
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stg = smem;                           // [2][T6_STG]
+  uint8_t* planes = stg + 2 * T6_STG;            // [2][3][T6_PLANE]
+  uint8_t* wring = planes + 2 * 3 * T6_PLANE;    // [WS][W_STAGE]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + WS * W_STAGE);
+  uint64_t* stg_full = bars;             // [2]
+  uint64_t* stg_empty = bars + 2;        // [2]
+  uint64_t* pl_full = bars + 4;          // [2]
+  uint64_t* pl_empty = bars + 6;         // [2]
+  uint64_t* w_full = bars + 8;           // [WS]
+  uint64_t* w_empty = w_full + WS;       // [WS]
+  uint64_t* accum_bar = w_empty + WS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  // tile coordinates
+  const int mt = blockIdx.x;
+  const int t0 = (mt % p.t_tiles) * p.t_sub;
+  const int b0 = (mt / p.t_tiles) * p.b_sub;
+  const int n0 = blockIdx.y * p.nj * BN;
+  const int nj = min(p.nj, (p.N - n0 + BN - 1) / BN);
+  const int num_kb = (p.K + T6_BK - 1) / T6_BK;
+  const int rows_box = p.t_sub * p.b_sub;
+  const int pm = min(p.pm, num_kb);          // accumulators actually written
+  const int acc_stride = p.nj * BN;          // columns per accumulator set
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < (1 + p.pm) * acc_stride) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&stg_full[s], 1);
+      mbar_init(&stg_empty[s], 8);
+      mbar_init(&pl_full[s], 8);
+      mbar_init(&pl_empty[s], 1);
+    }
+    for (int s = 0; s < WS; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------- A producer: f32 conv-window tile -> staging ----------------
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb & 1;
+      const uint32_t ph = (kb >> 1) & 1;
+      mbar_wait(&stg_empty[s], ph ^ 1);
+      const int kc = kb * T6_BK;
+      const int nsub = (p.K - kc > 32) ? 2 : 1;
+      mbar_expect_tx(&stg_full[s], (uint32_t)(nsub * rows_box * 128));
+      for (int h = 0; h < nsub; ++h)
+        tma_load_3d(stg + s * T6_STG + h * T6_STG_SUB, &map_a, kc + h * 32, t0, b0, &stg_full[s]);
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ---------------- W producer: three bf16 planes per (k-block, column sub-tile) ----------------
+    int it = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      for (int j = 0; j < nj; ++j, ++it) {
+        const int s = it % WS;
+        const uint32_t ph = (it / WS) & 1;
+        mbar_wait(&w_empty[s], ph ^ 1);
+        mbar_expect_tx(&w_full[s], (uint32_t)W_STAGE);
+        for (int q = 0; q < 3; ++q)
+          tma_load_3d(wring + s * W_STAGE + q * (BN * T6_BK * 2), &map_w, kb * T6_BK, n0 + j * BN, q, &w_full[s]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = make_idesc(BN);
+    // (a-plane, w-plane) pairs.  The tensor core truncates when it adds into the f32 accumulator, a
+    // bias that grows with the number of accumulations, so the five small cross terms go to their
+    // own accumulator (set 0) and the dominant a1*w1 term rotates over `pm` accumulators (sets 1..pm);
+    // the epilogue adds the sets in registers with round-to-nearest.
+    const int pa[6] = {0, 1, 2, 0, 1, 0};
+    const int pw[6] = {2, 1, 0, 1, 0, 0};
+    int it = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb & 1;
+      mbar_wait(&pl_full[s], (kb >> 1) & 1);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(planes + s * 3 * T6_PLANE);
+      for (int j = 0; j < nj; ++j, ++it) {
+        const int ws = it % WS;
+        mbar_wait(&w_full[ws], (it / WS) & 1);
+        tc_fence_after();
+        const uint32_t w_base = smem_u32(wring + ws * W_STAGE);
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+          const uint64_t da = make_smem_desc(a_base + pa[t] * T6_PLANE);
+          const uint64_t dw = make_smem_desc(w_base + pw[t] * (BN * T6_BK * 2));
+          const int set = t < 5 ? 0 : 1 + kb % pm;
+          const bool first = t < 5 ? (kb == 0 && t == 0) : (kb < pm);
+#pragma unroll
+          for (int k = 0; k < T6_BK / 16; ++k)
+            umma_bf16(tmem_base + set * acc_stride + j * BN, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc,
+                      (first && k == 0) ? 0u : 1u);
+        }
+        umma_commit(&w_empty[ws]);
+      }
+      umma_commit(&pl_empty[s]);
+    }
+    umma_commit(accum_bar);
+  } else if (warp >= 4) {
+    // ---------------- converters: staging f32 -> three swizzled bf16 operand tiles ----------------
+    const int cw = warp - 4;
+    const int r = (cw & 3) * 32 + lane;      // tile row
+    const int half = cw >> 2;                // which 32-wide half of the k-block
+    const int sw = r & 7;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb & 1;
+      const uint32_t ph = (kb >> 1) & 1;
+      const bool have = (p.K - kb * T6_BK > 32) || half == 0;
+      float4 v[8];
+      mbar_wait(&stg_full[s], ph);
+      if (have) {
+        const uint8_t* src = stg + s * T6_STG + half * T6_STG_SUB + r * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(src + ((c ^ sw) << 4));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&stg_empty[s]);      // staging slot may be refilled
+      mbar_wait(&pl_empty[s], ph ^ 1);                 // MMAs that read this plane buffer are done
+      uint8_t* dst = planes + s * 3 * T6_PLANE + r * 128;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const float4 x0 = v[2 * cc], x1 = v[2 * cc + 1];
+        __nv_bfloat16 a[8], b[8], c3[8];
+        split3(x0.x, a[0], b[0], c3[0]);
+        split3(x0.y, a[1], b[1], c3[1]);
+        split3(x0.z, a[2], b[2], c3[2]);
+        split3(x0.w, a[3], b[3], c3[3]);
+        split3(x1.x, a[4], b[4], c3[4]);
+        split3(x1.y, a[5], b[5], c3[5]);
+        split3(x1.z, a[6], b[6], c3[6]);
+        split3(x1.w, a[7], b[7], c3[7]);
+        const int chunk = ((half * 4 + cc) ^ sw) << 4;
+        *reinterpret_cast<uint4*>(dst + chunk) =
+            make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7]));
+        *reinterpret_cast<uint4*>(dst + T6_PLANE + chunk) =
+            make_uint4(pack2(b[0], b[1]), pack2(b[2], b[3]), pack2(b[4], b[5]), pack2(b[6], b[7]));
+        *reinterpret_cast<uint4*>(dst + 2 * T6_PLANE + chunk) =
+            make_uint4(pack2(c3[0], c3[1]), pack2(c3[2], c3[3]), pack2(c3[4], c3[5]), pack2(c3[6], c3[7]));
+      }
+      fence_proxy_async();      // make the generic-proxy stores visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pl_full[s]);
+    }
+  }
+
+  // ---------------- epilogue: all twelve warps ----------------
+  __syncwarp();
+  mbar_wait(accum_bar, 0);
+  tc_fence_after();
+  const int quad = warp & 3, grp = warp >> 2;
+  const int r = quad * 32 + lane;
+  const int bl = r / p.t_sub, tl = r - bl * p.t_sub;
+  const int b = b0 + bl, t = t0 + tl;
+  const bool row_ok = r < rows_box && b < p.B && t < p.T_out;
+  const int m = b * p.T_out + t;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+  const float* res_row = (p.res && row_ok) ? p.res + p.r_map.off(m) : nullptr;
+  float* raw_row = (p.out_raw && row_ok) ? p.out_raw + p.o_map.off(m) : nullptr;
+  float* act_row = (p.out_act && row_ok) ? p.out_act + p.e_map.off(m) : nullptr;
+  const int n_chunks = nj * BN / 32;
+#pragma unroll 1
+  for (int c = grp; c < n_chunks; c += 3) {
+    float v[32];
+    tmem_ld32(lane_addr + c * 32, v);
+    for (int a = 1; a <= pm; ++a) {
+      float u[32];
+      tmem_ld32(lane_addr + a * acc_stride + c * 32, u);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += u[i];
+    }
+    const int n = n0 + c * 32;
+    if (!row_ok || n >= p.N) continue;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float x = v[i];
+      if (p.bias) x = p.neg ? __ldg(p.bias + n + i) - x : x + __ldg(p.bias + n + i);
+      if (p.act == 1) x = gelu_erf(x);
+      if (p.scale) x *= __ldg(p.scale + n + i);
+      v[i] = x;
+    }
+    if (res_row) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(res_row + n + i);
+        v[i] += q.x, v[i + 1] += q.y, v[i + 2] += q.z, v[i + 3] += q.w;
+      }
+    }
+    if (raw_row) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(raw_row + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+    if (act_row) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(act_row + n + i) = make_float4(elu1(v[i]), elu1(v[i + 1]), elu1(v[i + 2]), elu1(v[i + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled6() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  DSM_CHECK(fn != nullptr, DSM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  return fn;
+}
+
+template <int BN>
+struct T6Cfg {
+  static constexpr int W_STAGE = 3 * BN * T6_BK * 2;
+  static constexpr int FIXED = 2 * T6_STG + 2 * 3 * T6_PLANE;             // 160 KB
+  static constexpr int WS_RAW = (212 * 1024 - FIXED) / W_STAGE;
+  static constexpr int WS = WS_RAW > 4 ? 4 : WS_RAW;
+  static constexpr int SMEM = FIXED + WS * W_STAGE + (9 + 2 * WS) * 8 + 16 + 1024;
+  static_assert(WS >= 2, "need at least two W stages");
+};
+
+template <int BN>
+static void launch6(const Tc6Gemm& g, cudaStream_t st) {
+  using C = T6Cfg<BN>;
+  auto kern = tc6_gemm_kernel<BN, C::WS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  Tc6Params p;
+  p.K = g.K, p.N = g.N, p.T_out = g.T_out, p.B = g.B, p.t_sub = g.t_sub, p.b_sub = g.b_sub;
+  p.t_tiles = ceil_div(g.T_out, g.t_sub), p.nj = g.nj, p.pm = g.pm;
+  p.bias = g.ep.bias, p.neg = g.ep.neg, p.scale = g.ep.scale, p.res = g.ep.res, p.r_map = g.ep.r_map, p.act = g.ep.act;
+  p.out_raw = g.ep.out_raw, p.o_map = g.ep.o_map, p.out_act = g.ep.out_act, p.e_map = g.ep.e_map;
+  dim3 grid(p.t_tiles * ceil_div(g.B, g.b_sub), ceil_div(g.N, g.nj * BN));
+  kern<<<grid, T6_THREADS, C::SMEM, st>>>(g.map_a, g.map_w, p);
+  check_launch("tc6_gemm");
+}
+
+bool tc6_supported(const GemmParams& g) {
+  if (g.M <= 0 || g.N % 32 != 0 || g.K % 32 != 0 || g.out_bf16) return false;
+  if (g.a_map.T <= 0 || g.M % g.a_map.T != 0) return false;
+  // TMA: strides in bytes must be multiples of 16
+  if ((g.a_map.stride_t * 4) % 16 != 0 || (g.a_map.stride_b * 4) % 16 != 0) return false;
+  if (reinterpret_cast<uintptr_t>(g.A) % 16 != 0) return false;
+  return true;
+}
+
+__nv_bfloat16* tc6_split_weights(Arena& arena, const std::vector<float>& w, int N, int K) {
+  DSM_CHECK((size_t)N * K == w.size(), DSM_ERR_SHAPE, "tc6_split_weights: %d x %d != %zu", N, K, w.size());
+  std::vector<uint16_t> planes((size_t)3 * N * K);
+  auto to_bf16 = [](float x) -> uint16_t {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+  };
+  auto from_bf16 = [](uint16_t h) -> float {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  };
+  const size_t n = (size_t)N * K;
+  for (size_t i = 0; i < n; ++i) {
+    const float x = w[i];
+    const uint16_t b1 = to_bf16(x);
+    const float r1 = x - from_bf16(b1);
+    const uint16_t b2 = to_bf16(r1);
+    const float r2 = r1 - from_bf16(b2);
+    planes[i] = b1, planes[n + i] = b2, planes[2 * n + i] = to_bf16(r2);
+  }
+  __nv_bfloat16* d = arena.alloc<__nv_bfloat16>(3 * n, false);
+  DSM_CUDA(cudaMemcpy(d, planes.data(), 3 * n * 2, cudaMemcpyHostToDevice));
+  return d;
+}
+
+void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes) {
+  DSM_CHECK(tc6_supported(g), DSM_ERR_UNSUPPORTED, "tc6_gemm: unsupported problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  t.ep = g;
+  t.K = g.K, t.N = g.N, t.T_out = g.a_map.T, t.B = g.M / g.a_map.T;
+  // rows of a tile: a run of time steps of one stream, or whole (short) streams side by side
+  if (t.T_out >= T6_BM || T6_BM % t.T_out != 0) t.t_sub = std::min(t.T_out, T6_BM), t.b_sub = 1;
+  else t.t_sub = t.T_out, t.b_sub = T6_BM / t.T_out;
+  t.bn = g.N % 64 == 0 ? 64 : 32;
+  const long long m_tiles = (long long)ceil_div(t.T_out, t.t_sub) * ceil_div(t.B, t.b_sub);
+  const int n_sub = ceil_div(g.N, t.bn);
+  // column sub-tiles per CTA: as many as TMEM holds (512 columns) while the grid still covers the SMs
+  // (TMEM: 512 columns shared by the correction accumulator and >= 1 main accumulator => <= 256 columns)
+  int nj = std::min(n_sub, 256 / t.bn);
+  while (nj > 1 && m_tiles * ceil_div(n_sub, nj) < 148) nj = (nj + 1) / 2;
+  t.nj = nj;
+  t.pm = std::max(1, std::min(7, 512 / (nj * t.bn) - 1));
+  // A: f32 [B][T_out][K] window view, box 32 x t_sub x b_sub
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)g.K, (cuuint64_t)t.T_out, (cuuint64_t)t.B};
+    cuuint64_t gstr[2] = {(cuuint64_t)g.a_map.stride_t * 4, (cuuint64_t)g.a_map.stride_b * 4};
+    if (t.T_out == 1) gstr[0] = gstr[1];      // degenerate time dimension: any legal stride
+    cuuint32_t box[3] = {32, (cuuint32_t)t.t_sub, (cuuint32_t)t.b_sub};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode_tiled6()(&t.map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(g.A), gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DSM_CHECK(r == CUDA_SUCCESS, DSM_ERR_CUDA, "tc6 A tensor map failed (%d): K=%d T=%d B=%d strides %lld %lld", (int)r, g.K,
+              t.T_out, t.B, (long long)gstr[0], (long long)gstr[1]);
+  }
+  // W: bf16 [3][N][K] planes, box 64 x bn x 1
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)g.K, (cuuint64_t)g.N, 3};
+    cuuint64_t gstr[2] = {(cuuint64_t)g.K * 2, (cuuint64_t)g.K * g.N * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)t.bn, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode_tiled6()(&t.map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(w_planes), gdim, gstr,
+                                 box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DSM_CHECK(r == CUDA_SUCCESS, DSM_ERR_CUDA, "tc6 W tensor map failed (%d): N=%d K=%d", (int)r, g.N, g.K);
+  }
+}
+
+void tc6_launch(const Tc6Gemm& t, cudaStream_t st) {
+  if (t.bn == 64) return launch6<64>(t, st);
+  return launch6<32>(t, st);
+}
+
+}  // namespace dsm

@@ -29,12 +29,40 @@ static std::vector<float> rope_inv_freq(int head_dim, float theta) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// codec GEMM dispatch
+// ---------------------------------------------------------------------------------------------
+bool codec_gemm_tc_enabled() {
+  const char* e = getenv("DSM_CODEC_GEMM");
+  return !(e && std::string(e) == "simt");
+}
+
+std::shared_ptr<CodecGemm> make_codec_gemm(Arena& arena, const GemmParams& g, const std::vector<float>& w_host) {
+  auto c = std::make_shared<CodecGemm>();
+  c->g = g;
+  DSM_CHECK(w_host.size() == (size_t)g.N * g.K, DSM_ERR_SHAPE, "codec gemm: weight has %zu elements, expected %d x %d",
+            w_host.size(), g.N, g.K);
+  c->use_tc = codec_gemm_tc_enabled() && tc6_supported(g);
+  if (c->use_tc) {
+    tc6_prepare(c->t, g, tc6_split_weights(arena, w_host, g.N, g.K));
+  } else {
+    c->g.W = arena.upload(w_host);
+  }
+  return c;
+}
+
+void run_codec_gemm(const CodecGemm& c, cudaStream_t st) {
+  if (c.use_tc) tc6_launch(c.t, st);
+  else launch_gemm_simt<float, float>(c.g, st);
+}
+
+// ---------------------------------------------------------------------------------------------
 // codec transformer
 // ---------------------------------------------------------------------------------------------
 void CodecTransformer::init(Arena& arena, const dsm_mimi_spec& s, int batch, const std::string& prefix,
                             const GetFn& get) {
   B = batch, T = 2, D = s.dim, H = s.num_heads, hd = D / H, ff = s.dim_feedforward, ctx = s.context, L = s.num_layers;
   eps = s.ln_eps;
+  arena_ = &arena;
   DSM_CHECK(hd == 64 && D == 512, DSM_ERR_UNSUPPORTED, "codec transformer: d_model %d / heads %d (need 512 / 64-wide)", D, H);
   ring.positions = arena.alloc<uint32_t>(B);
   ring.indices = arena.alloc<uint32_t>(B);
@@ -52,15 +80,15 @@ void CodecTransformer::init(Arena& arena, const dsm_mimi_spec& s, int batch, con
   for (int l = 0; l < L; ++l) {
     const std::string p = prefix + ".transformer.layers." + std::to_string(l);
     Layer& y = layers[l];
-    y.in_proj = arena.upload(get(p + ".self_attn.in_proj_weight", (size_t)3 * D * D, sd, 0.f));
-    y.out_proj = arena.upload(get(p + ".self_attn.out_proj.weight", (size_t)D * D, sd, 0.f));
+    y.h_in_proj = get(p + ".self_attn.in_proj_weight", (size_t)3 * D * D, sd, 0.f);
+    y.h_out_proj = get(p + ".self_attn.out_proj.weight", (size_t)D * D, sd, 0.f);
     // LayerNorm weight is stored as `alpha` or `weight` (batched_transformer.rs:206-212)
     y.ln1w = arena.upload(get(p + ".norm1.alpha|" + p + ".norm1.weight", D, 0.1f, 1.f));
     y.ln1b = arena.upload(get(p + ".norm1.bias", D, 0.05f, 0.f));
     y.ln2w = arena.upload(get(p + ".norm2.alpha|" + p + ".norm2.weight", D, 0.1f, 1.f));
     y.ln2b = arena.upload(get(p + ".norm2.bias", D, 0.05f, 0.f));
-    y.lin1 = arena.upload(get(p + ".linear1.weight", (size_t)ff * D, sd, 0.f));
-    y.lin2 = arena.upload(get(p + ".linear2.weight", (size_t)D * ff, sff, 0.f));
+    y.h_lin1 = get(p + ".linear1.weight", (size_t)ff * D, sd, 0.f);
+    y.h_lin2 = get(p + ".linear2.weight", (size_t)D * ff, sff, 0.f);
     y.ls1 = arena.upload(get(p + ".layer_scale_1.scale", D, 0.f, 0.01f));
     y.ls2 = arena.upload(get(p + ".layer_scale_2.scale", D, 0.f, 0.01f));
     const size_t ring_elems = (size_t)B * H * ctx * hd;
@@ -75,32 +103,39 @@ void CodecTransformer::append_plan(Plan& plan, float* x, RowMap x_map, const uin
   CodecTransformer* self = this;
   plan.push_back([=](cudaStream_t st) { launch_ring_advance(self->ring, d_mask, self->B, self->T, self->ctx, st); });
   for (int l = 0; l < L; ++l) {
-    const Layer y = layers[l];
+    Layer& yl = layers[l];
+    GemmParams g;     // qkv = in_proj(norm1(x))
+    g.A = xn, g.a_map = dense_rows(1, D), g.M = M, g.N = 3 * D, g.K = D;
+    g.out_raw = qkv, g.o_map = dense_rows(1, 3 * D);
+    auto g_qkv = make_codec_gemm(*arena_, g, yl.h_in_proj);
+    GemmParams o;     // x <- x + layer_scale_1 * out_proj(attn)     (batched_transformer.rs:347-349)
+    o.A = attn, o.a_map = dense_rows(1, D), o.M = M, o.N = D, o.K = D;
+    o.scale = yl.ls1, o.res = x, o.r_map = x_map, o.out_raw = x, o.o_map = x_map;
+    auto g_out = make_codec_gemm(*arena_, o, yl.h_out_proj);
+    GemmParams f1;    // h = gelu(linear1(norm2(x)))
+    f1.A = xn, f1.a_map = dense_rows(1, D), f1.M = M, f1.N = ff, f1.K = D;
+    f1.act = 1, f1.out_raw = hbuf, f1.o_map = dense_rows(1, ff);
+    auto g_f1 = make_codec_gemm(*arena_, f1, yl.h_lin1);
+    GemmParams f2;    // x <- x + layer_scale_2 * linear2(h)   (:360-361)
+    f2.A = hbuf, f2.a_map = dense_rows(1, ff), f2.M = M, f2.N = D, f2.K = ff;
+    f2.scale = yl.ls2, f2.res = x, f2.r_map = x_map, f2.out_raw = x, f2.o_map = x_map;
+    auto g_f2 = make_codec_gemm(*arena_, f2, yl.h_lin2);
+    yl.h_in_proj = std::vector<float>();
+    yl.h_out_proj = std::vector<float>();
+    yl.h_lin1 = std::vector<float>();
+    yl.h_lin2 = std::vector<float>();
+    const Layer y = yl;
     plan.push_back([=](cudaStream_t st) {
       launch_layernorm(x, x_map, y.ln1w, y.ln1b, self->eps, M, self->D, self->xn, st);
-      GemmParams g;
-      g.A = self->xn, g.a_map = dense_rows(1, self->D), g.W = y.in_proj, g.M = M, g.N = 3 * self->D, g.K = self->D;
-      g.out_raw = self->qkv, g.o_map = dense_rows(1, 3 * self->D);
-      launch_gemm_simt<float, float>(g, st);
+      run_codec_gemm(*g_qkv, st);
       launch_rope_scatter_f32(self->qkv, self->ring, d_mask, self->B, self->T, self->H, self->hd, self->ctx,
                               self->inv_freq, y.k_ring, y.v_ring, st);
       launch_codec_attention(self->qkv, self->ring, d_mask, self->B, self->T, self->H, self->hd, self->ctx, y.k_ring,
                              y.v_ring, self->attn, st);
-      // x <- x + layer_scale_1 * out_proj(attn)     (batched_transformer.rs:347-349)
-      GemmParams o;
-      o.A = self->attn, o.a_map = dense_rows(1, self->D), o.W = y.out_proj, o.M = M, o.N = self->D, o.K = self->D;
-      o.scale = y.ls1, o.res = x, o.r_map = x_map, o.out_raw = x, o.o_map = x_map;
-      launch_gemm_simt<float, float>(o, st);
+      run_codec_gemm(*g_out, st);
       launch_layernorm(x, x_map, y.ln2w, y.ln2b, self->eps, M, self->D, self->xn, st);
-      GemmParams f1;
-      f1.A = self->xn, f1.a_map = dense_rows(1, self->D), f1.W = y.lin1, f1.M = M, f1.N = self->ff, f1.K = self->D;
-      f1.act = 1, f1.out_raw = self->hbuf, f1.o_map = dense_rows(1, self->ff);
-      launch_gemm_simt<float, float>(f1, st);
-      // x <- x + layer_scale_2 * linear2(gelu(linear1(norm2(x))))   (:360-361)
-      GemmParams f2;
-      f2.A = self->hbuf, f2.a_map = dense_rows(1, self->ff), f2.W = y.lin2, f2.M = M, f2.N = self->D, f2.K = self->ff;
-      f2.scale = y.ls2, f2.res = x, f2.r_map = x_map, f2.out_raw = x, f2.o_map = x_map;
-      launch_gemm_simt<float, float>(f2, st);
+      run_codec_gemm(*g_f1, st);
+      run_codec_gemm(*g_f2, st);
     });
   }
 }
@@ -248,20 +283,20 @@ static void build_seanet(const SeanetBuild& sb, const std::vector<SeanetLayer>& 
     const bool last = i == n - 1;
     const float wstd = 1.4f / sqrtf((float)(y.cin * y.k)) * (y.tr ? sqrtf((float)y.stride) : 1.f);
     // ---- weights ----
-    float* dW = nullptr;
+    std::vector<float> hW;     // GEMM layout [N][K]
     float* dBias = nullptr;
     {
       std::vector<float> bias = (*sb.get)(y.wname + ".bias", y.cout, 0.05f, 0.f);
       if (y.tr) {
         std::vector<float> w = folded_weight(*sb.get, *sb.wt, y.wname, y.cin, y.cout, y.k, wstd);
-        dW = arena.upload(convtr_to_gemm(w, y.cin, y.cout, y.k, y.stride));
+        hW = convtr_to_gemm(w, y.cin, y.cout, y.k, y.stride);
         std::vector<float> b2((size_t)N[i]);
         for (int r = 0; r < y.stride; ++r)
           for (int co = 0; co < y.cout; ++co) b2[(size_t)r * y.cout + co] = bias[co];
         dBias = arena.upload(b2);
       } else {
         std::vector<float> w = folded_weight(*sb.get, *sb.wt, y.wname, y.cout, y.cin, y.k, wstd);
-        dW = arena.upload(conv_to_gemm(w, y.cout, y.cin, y.k));
+        hW = conv_to_gemm(w, y.cout, y.cin, y.k);
         dBias = arena.upload(bias);
       }
     }
@@ -295,6 +330,7 @@ static void build_seanet(const SeanetBuild& sb, const std::vector<SeanetLayer>& 
     if (i == 0 && !first_in) {
       DSM_CHECK(y.cin == 1 && !y.tr, DSM_ERR_UNSUPPORTED, "first layer without an input buffer must have C_in = 1");
       const int S0 = S[0], T_in = T[0], C = y.cout, k = y.k;
+      float* dW = arena.upload(hW);
       sb.plan->push_back([=](cudaStream_t st) {
         launch_init_conv(pcm_in, state0, S0, dW, dBias, B, T_in, C, k, out_raw, raw_map, out_act, act_map, st);
       });
@@ -303,17 +339,19 @@ static void build_seanet(const SeanetBuild& sb, const std::vector<SeanetLayer>& 
       const RowMap xm{T[i + 1], (long long)(S[i] + T[i]) * y.cin, (long long)seff[i] * y.cin};
       const float* xin = X[i];
       const int Tn = T[i + 1], C = y.cin, k = y.k;
+      float* dW = arena.upload(hW);
       sb.plan->push_back([=](cudaStream_t st) { launch_final_conv(xin, xm, dW, dBias, B, Tn, C, k, pcm_out, st); });
     } else {
       GemmParams g;
       g.A = X[i];
       g.a_map = RowMap{rows, (long long)(S[i] + T[i]) * y.cin, (long long)seff[i] * y.cin};
-      g.W = dW, g.M = B * rows, g.N = N[i], g.K = keff[i] * y.cin;
+      g.M = B * rows, g.N = N[i], g.K = keff[i] * y.cin;
       g.bias = dBias;
       g.res = res, g.r_map = res_map;
       g.out_raw = out_raw, g.o_map = raw_map;
       g.out_act = out_act, g.e_map = act_map;
-      sb.plan->push_back([=](cudaStream_t st) { launch_gemm_simt<float, float>(g, st); });
+      auto cg = make_codec_gemm(arena, g, hW);
+      sb.plan->push_back([=](cudaStream_t st) { run_codec_gemm(*cg, st); });
     }
   }
 }
@@ -440,18 +478,17 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
   // ---- downsample conv (conv.rs:505-534: k = 2*stride, no bias, replicate pad on the first step) ----
   {
     std::vector<float> w = get("downsample.conv.conv.conv.weight", (size_t)D * D * 2 * ds, 1.f / sqrtf((float)D * 2 * ds), 0.f);
-    float* dW = arena.upload(conv_to_gemm(w, D, D, 2 * ds));
+    GemmParams g;
+    g.A = x_ds, g.a_map = RowMap{1, (long long)(Sds + Tds) * D, (long long)ds * D};
+    g.M = Bc, g.N = D, g.K = 2 * ds * D;
+    g.out_raw = latent, g.o_map = dense_rows(1, D);
+    auto cg = make_codec_gemm(arena, g, conv_to_gemm(w, D, D, 2 * ds));
     enc_commits.push_back(CommitEntry{x_ds, x_ds + (long long)Tds * D, (long long)(Sds + Tds) * D, (long long)(Sds + Tds) * D, Sds * D, 1});
     float* xds = x_ds;
     int* first = d_first_step;
-    float* lat = latent;
     enc_plan.push_back([=](cudaStream_t st) {
       launch_replicate_pad(xds, (long long)(Sds + Tds) * D, Sds, D, first, Bc, st);
-      GemmParams g;
-      g.A = xds, g.a_map = RowMap{1, (long long)(Sds + Tds) * D, (long long)ds * D};
-      g.W = dW, g.M = Bc, g.N = D, g.K = 2 * ds * D;
-      g.out_raw = lat, g.o_map = dense_rows(1, D);
-      launch_gemm_simt<float, float>(g, st);
+      run_codec_gemm(*cg, st);
     });
   }
   // ---- split RVQ encode (quantization.rs:366-378) ----
@@ -462,27 +499,32 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
     std::vector<float> wr = nq > 1 ? get("quantizer.rvq_rest.input_proj.weight", (size_t)qd * D, 1.f / sqrtf((float)D), 0.f)
                                    : std::vector<float>((size_t)qd * D, 0.f);
     wf.insert(wf.end(), wr.begin(), wr.end());
-    float* dWp = arena.upload(wf);
-    float* lat = latent;
+    GemmParams gp;
+    gp.A = latent, gp.a_map = dense_rows(1, D), gp.M = Bc, gp.N = 2 * qd, gp.K = D;
+    gp.out_raw = resid, gp.o_map = dense_rows(1, 2 * qd);
+    auto g_proj = make_codec_gemm(arena, gp, wf);
+    // codebook embeddings on the host once more for the score GEMMs' weight planes
+    std::vector<float> emb_host((size_t)nq * bins * qd);
+    DSM_CUDA(cudaMemcpy(emb_host.data(), emb_all, emb_host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    std::vector<std::shared_ptr<CodecGemm>> g_score(nq);
+    for (int q = 0; q < nq; ++q) {
+      GemmParams s;
+      s.A = resid + (q == 0 ? 0 : qd), s.a_map = RowMap{1, (long long)2 * qd, (long long)2 * qd};
+      s.M = Bc, s.N = bins, s.K = qd;
+      s.bias = c2_all + (size_t)q * bins, s.neg = 1;     // c2 - x.e   (quantization.rs:128-129)
+      s.out_raw = scores, s.o_map = dense_rows(1, bins);
+      std::vector<float> Eq(emb_host.begin() + (size_t)q * bins * qd, emb_host.begin() + (size_t)(q + 1) * bins * qd);
+      g_score[q] = make_codec_gemm(arena, s, Eq);
+    }
     float* res = resid;
     float* sc = scores;
     float* emb = emb_all;
-    float* c2 = c2_all;
     uint32_t* codes = d_codes;
     enc_plan.push_back([=](cudaStream_t st) {
-      GemmParams g;
-      g.A = lat, g.a_map = dense_rows(1, D), g.W = dWp, g.M = Bc, g.N = 2 * qd, g.K = D;
-      g.out_raw = res, g.o_map = dense_rows(1, 2 * qd);
-      launch_gemm_simt<float, float>(g, st);
+      run_codec_gemm(*g_proj, st);
       for (int q = 0; q < nq; ++q) {
-        float* r = res + (q == 0 ? 0 : qd);
-        const float* E = emb + (size_t)q * bins * qd;
-        GemmParams s;
-        s.A = r, s.a_map = RowMap{1, (long long)2 * qd, 0}, s.W = E, s.M = Bc, s.N = bins, s.K = qd;
-        s.bias = c2 + (size_t)q * bins, s.neg = 1;     // c2 - x.e   (quantization.rs:128-129)
-        s.out_raw = sc, s.o_map = dense_rows(1, bins);
-        launch_gemm_simt<float, float>(s, st);
-        launch_rvq_select(sc, Bc, bins, E, qd, r, 2 * qd, codes, nq, q, st);
+        run_codec_gemm(*g_score[q], st);
+        launch_rvq_select(sc, Bc, bins, emb + (size_t)q * bins * qd, qd, res + (q == 0 ? 0 : qd), 2 * qd, codes, nq, q, st);
       }
     });
   }
@@ -529,20 +571,20 @@ void MimiImpl::build_decoder(const GetFn& get, const WeightTable& wt) {
     float* ups = up_state;
     // dec_emb = Wf . q_first + Wr . q_rest, each projection on its own dense [B, qd] gather buffer
     // (quantization.rs:380-390 decodes the two groups separately and adds)
-    float* dWf = arena.upload(wf);
-    float* dWr = arena.upload(wr);
+    GemmParams g1;
+    g1.A = q_sum, g1.a_map = dense_rows(1, qd), g1.M = Bc, g1.N = D, g1.K = qd;
+    g1.out_raw = dec_emb, g1.o_map = dense_rows(1, D);
+    auto cg1 = make_codec_gemm(arena, g1, wf);
+    GemmParams g2;
+    g2.A = q_sum + (size_t)Bc * qd, g2.a_map = dense_rows(1, qd), g2.M = Bc, g2.N = D, g2.K = qd;
+    g2.res = dec_emb, g2.r_map = dense_rows(1, D), g2.out_raw = dec_emb, g2.o_map = dense_rows(1, D);
+    auto cg2 = make_codec_gemm(arena, g2, wr);
     dec_plan.push_back([=](cudaStream_t st) {
       launch_rvq_gather_sum(cin, nq, 0, 1, emb, bins, qd, Bc, qs, st);
-      GemmParams g1;
-      g1.A = qs, g1.a_map = dense_rows(1, qd), g1.W = dWf, g1.M = Bc, g1.N = D, g1.K = qd;
-      g1.out_raw = de, g1.o_map = dense_rows(1, D);
-      launch_gemm_simt<float, float>(g1, st);
+      run_codec_gemm(*cg1, st);
       if (nq > 1) {
         launch_rvq_gather_sum(cin, nq, 1, nq, emb, bins, qd, Bc, qs + (size_t)Bc * qd, st);
-        GemmParams g2;
-        g2.A = qs + (size_t)Bc * qd, g2.a_map = dense_rows(1, qd), g2.W = dWr, g2.M = Bc, g2.N = D, g2.K = qd;
-        g2.res = de, g2.r_map = dense_rows(1, D), g2.out_raw = de, g2.o_map = dense_rows(1, D);
-        launch_gemm_simt<float, float>(g2, st);
+        run_codec_gemm(*cg2, st);
       }
       launch_upsample_dw(de, ups, dWu, Bc, D, ds, x, x_map, st);
     });

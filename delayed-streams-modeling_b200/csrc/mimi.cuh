@@ -6,10 +6,22 @@
 #include <vector>
 
 #include "gemm_simt.cuh"
+#include "gemm_tc6.cuh"
 #include "kernels.cuh"
 #include "runtime.cuh"
 
 namespace dsm {
+
+// One codec GEMM: runs on the tcgen05 split-bf16 kernel (f32-accurate) or on the CUDA-core kernel
+// (DSM_CODEC_GEMM=simt, or shapes the tensor-core kernel does not take).
+struct CodecGemm {
+  GemmParams g;      // g.W = f32 weights [N, K] on the device
+  Tc6Gemm t;
+  bool use_tc = false;
+};
+bool codec_gemm_tc_enabled();
+std::shared_ptr<CodecGemm> make_codec_gemm(Arena& arena, const GemmParams& g, const std::vector<float>& w_host);
+void run_codec_gemm(const CodecGemm& c, cudaStream_t st);
 
 // One f32 streaming transformer with per-stream ring KV (batched_transformer.rs, Mimi flavour:
 // LayerNorm, GELU MLP, LayerScale, RoPE).
@@ -20,9 +32,11 @@ struct CodecTransformer {
   float* inv_freq = nullptr;
   float *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr;
   struct Layer {
-    float *in_proj, *out_proj, *ln1w, *ln1b, *ln2w, *ln2b, *lin1, *lin2, *ls1, *ls2;
+    float *ln1w, *ln1b, *ln2w, *ln2b, *ls1, *ls2;
     float *k_ring, *v_ring;
+    std::vector<float> h_in_proj, h_out_proj, h_lin1, h_lin2;   // host copies until the plan is built
   };
+  Arena* arena_ = nullptr;
   std::vector<Layer> layers;
   size_t kv_bytes = 0;
 

@@ -122,6 +122,12 @@ void dsm_launch_count_reset(void);
 dsm_status dsm_debug_gemm_bf16(int32_t impl, int32_t mode, int32_t M, int32_t N, int32_t K, const uint16_t* X,
                                const uint16_t* W, float* inout_f32, uint16_t* out_bf16);
 
+/* Stand-alone check of the codec GEMM kernels on device 0: out[(b,t), n] = bias[n] + sum_k
+ * A[b*stride_b + t*stride_t + k] * W[n,k] (the implicit-GEMM streaming-conv window, conv.rs:342), f32,
+ * through the CUDA-core kernel (impl 0) or the tcgen05 3-way-bf16-split kernel (impl 1). */
+dsm_status dsm_debug_gemm_f32(int32_t impl, int32_t B, int32_t T, int64_t stride_b, int64_t stride_t, int32_t N, int32_t K,
+                              const float* A, int64_t a_elems, const float* W, const float* bias, float* out);
+
 void dsm_mimi_spec_v0_1(dsm_mimi_spec* spec, int32_t n_q);            /* mimi.rs:32 Config::v0_1 */
 void dsm_lm_spec_stt_1b_en_fr(dsm_lm_spec* spec);                     /* config-stt-en_fr-hf.toml */
 void dsm_lm_spec_stt_2_6b_en(dsm_lm_spec* spec);                      /* config-stt-en-hf.toml */
