@@ -100,6 +100,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// ELU as the reference computes it: exp(x) - 1 for x <= 0 (candle Activation::Elu), not expm1
+__device__ __forceinline__ float elu_ref(float x) { return x > 0.f ? x : expf(x) - 1.f; }
 // K-major SWIZZLE_128B tile with 128-byte rows (see gemm_tc.cu)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -114,24 +129,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-// x = b1 + b2 + b3 (+ <= 2^-24 |x|), each term a bf16
-__device__ __forceinline__ void split3(float x, __nv_bfloat16& b1, __nv_bfloat16& b2, __nv_bfloat16& b3) {
-  b1 = __float2bfloat16_rn(x);
-  const float r1 = x - __bfloat162float(b1);
-  b2 = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(b2);
-  b3 = __float2bfloat16_rn(r2);
-}
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
-  return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
-}
-
 constexpr int T6_BM = 128;           // rows per CTA (UMMA M)
 constexpr int T6_BK = 64;            // K elements per k-block
 constexpr int T6_STG_SUB = T6_BM * 32 * 4;       // one staging sub-tile: 128 rows x 32 f32 (128-byte rows)
 constexpr int T6_STG = 2 * T6_STG_SUB;           // 32 KB per k-block
 constexpr int T6_PLANE = T6_BM * T6_BK * 2;      // 16 KB per bf16 plane tile
-constexpr int T6_THREADS = 384;
+constexpr int T6_EPI_WARPS = 8;      // two per TMEM lane quadrant
+constexpr int T6_THREADS = (12 + T6_EPI_WARPS) * 32;
 
 }  // namespace
 
@@ -140,7 +144,9 @@ struct Tc6Params {
   int T_out, B;        // logical rows = B * T_out, row m = b * T_out + t
   int t_sub, b_sub;    // rows of one tile = t_sub * b_sub (<= 128)
   int t_tiles;         // ceil(T_out / t_sub)
-  int nj;              // column sub-tiles per CTA
+  int m_tiles;         // t_tiles * ceil(B / b_sub)
+  int n_groups;        // ceil(N / (nj * BN))
+  int nj;              // column sub-tiles per tile
   int pm;              // main-term accumulators the k-blocks rotate over (see the MMA issuer)
   const float* bias;
   int neg;
@@ -154,6 +160,8 @@ struct Tc6Params {
   RowMap e_map;
 };
 
+// Persistent: gridDim.x CTAs (<= one per SM) walk the tiles; TMEM holds two accumulator buffers so the
+// epilogue warps drain tile i while the producers / converters / MMA issuer are already on tile i+1.
 template <int BN, int WS>
 __global__ void __launch_bounds__(T6_THREADS, 1)
 tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Tc6Params p) {
@@ -163,29 +171,25 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint8_t* stg = smem;                           // [2][T6_STG]
   uint8_t* planes = stg + 2 * T6_STG;            // [2][3][T6_PLANE]
   uint8_t* wring = planes + 2 * 3 * T6_PLANE;    // [WS][W_STAGE]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + WS * W_STAGE);
+  float* scratch_all = reinterpret_cast<float*>(wring + WS * W_STAGE);   // [epilogue warps][32][17]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + T6_EPI_WARPS * 32 * 17);
   uint64_t* stg_full = bars;             // [2]
   uint64_t* stg_empty = bars + 2;        // [2]
   uint64_t* pl_full = bars + 4;          // [2]
   uint64_t* pl_empty = bars + 6;         // [2]
-  uint64_t* w_full = bars + 8;           // [WS]
+  uint64_t* acc_full = bars + 8;         // [2]
+  uint64_t* acc_empty = bars + 10;       // [2]
+  uint64_t* w_full = bars + 12;          // [WS]
   uint64_t* w_empty = w_full + WS;       // [WS]
-  uint64_t* accum_bar = w_empty + WS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + WS);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  // tile coordinates
-  const int mt = blockIdx.x;
-  const int t0 = (mt % p.t_tiles) * p.t_sub;
-  const int b0 = (mt / p.t_tiles) * p.b_sub;
-  const int n0 = blockIdx.y * p.nj * BN;
-  const int nj = min(p.nj, (p.N - n0 + BN - 1) / BN);
   const int num_kb = (p.K + T6_BK - 1) / T6_BK;
   const int rows_box = p.t_sub * p.b_sub;
-  const int pm = min(p.pm, num_kb);          // accumulators actually written
-  const int acc_stride = p.nj * BN;          // columns per accumulator set
-  uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < (1 + p.pm) * acc_stride) tmem_cols <<= 1;
+  const int pm = min(p.pm, num_kb);          // main accumulators actually written
+  const int acc_stride = p.nj * BN;          // columns of one accumulator set
+  const int buf_stride = (1 + p.pm) * acc_stride;   // columns of one tile's accumulators (<= 256)
+  const int total_tiles = p.m_tiles * p.n_groups;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -197,15 +201,16 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_init(&stg_empty[s], 8);
       mbar_init(&pl_full[s], 8);
       mbar_init(&pl_empty[s], 1);
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], T6_EPI_WARPS);
     }
     for (int s = 0; s < WS; ++s) {
       mbar_init(&w_full[s], 1);
       mbar_init(&w_empty[s], 1);
     }
-    mbar_init(accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -213,27 +218,34 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     // ---------------- A producer: f32 conv-window tile -> staging ----------------
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb & 1;
-      const uint32_t ph = (kb >> 1) & 1;
-      mbar_wait(&stg_empty[s], ph ^ 1);
-      const int kc = kb * T6_BK;
-      const int nsub = (p.K - kc > 32) ? 2 : 1;
-      mbar_expect_tx(&stg_full[s], (uint32_t)(nsub * rows_box * 128));
-      for (int h = 0; h < nsub; ++h)
-        tma_load_3d(stg + s * T6_STG + h * T6_STG_SUB, &map_a, kc + h * 32, t0, b0, &stg_full[s]);
+    int kit = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_groups;
+      const int t0 = (mt % p.t_tiles) * p.t_sub, b0 = (mt / p.t_tiles) * p.b_sub;
+      for (int kb = 0; kb < num_kb; ++kb, ++kit) {
+        const int s = kit & 1;
+        mbar_wait(&stg_empty[s], ((kit >> 1) & 1) ^ 1);
+        const int kc = kb * T6_BK;
+        const int nsub = (p.K - kc > 32) ? 2 : 1;
+        mbar_expect_tx(&stg_full[s], (uint32_t)(nsub * rows_box * 128));
+        for (int h = 0; h < nsub; ++h)
+          tma_load_3d(stg + s * T6_STG + h * T6_STG_SUB, &map_a, kc + h * 32, t0, b0, &stg_full[s]);
+      }
     }
   } else if (warp == 3 && lane == 0) {
     // ---------------- W producer: three bf16 planes per (k-block, column sub-tile) ----------------
-    int it = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      for (int j = 0; j < nj; ++j, ++it) {
-        const int s = it % WS;
-        const uint32_t ph = (it / WS) & 1;
-        mbar_wait(&w_empty[s], ph ^ 1);
-        mbar_expect_tx(&w_full[s], (uint32_t)W_STAGE);
-        for (int q = 0; q < 3; ++q)
-          tma_load_3d(wring + s * W_STAGE + q * (BN * T6_BK * 2), &map_w, kb * T6_BK, n0 + j * BN, q, &w_full[s]);
+    int wit = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n0 = (tile % p.n_groups) * p.nj * BN;
+      const int nj = min(p.nj, (p.N - n0 + BN - 1) / BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        for (int j = 0; j < nj; ++j, ++wit) {
+          const int s = wit % WS;
+          mbar_wait(&w_empty[s], ((wit / WS) & 1) ^ 1);
+          mbar_expect_tx(&w_full[s], (uint32_t)W_STAGE);
+          for (int q = 0; q < 3; ++q)
+            tma_load_3d(wring + s * W_STAGE + q * (BN * T6_BK * 2), &map_w, kb * T6_BK, n0 + j * BN, q, &w_full[s]);
+        }
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -245,139 +257,187 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // the epilogue adds the sets in registers with round-to-nearest.
     const int pa[6] = {0, 1, 2, 0, 1, 0};
     const int pw[6] = {2, 1, 0, 1, 0, 0};
-    int it = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb & 1;
-      mbar_wait(&pl_full[s], (kb >> 1) & 1);
+    int kit = 0, wit = 0, li = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+      const int n0 = (tile % p.n_groups) * p.nj * BN;
+      const int nj = min(p.nj, (p.N - n0 + BN - 1) / BN);
+      const int buf = li & 1;
+      mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1);     // epilogue has drained this TMEM buffer
       tc_fence_after();
-      const uint32_t a_base = smem_u32(planes + s * 3 * T6_PLANE);
-      for (int j = 0; j < nj; ++j, ++it) {
-        const int ws = it % WS;
-        mbar_wait(&w_full[ws], (it / WS) & 1);
+      const uint32_t acc_base = tmem_base + buf * buf_stride;
+      for (int kb = 0; kb < num_kb; ++kb, ++kit) {
+        const int s = kit & 1;
+        mbar_wait(&pl_full[s], (kit >> 1) & 1);
         tc_fence_after();
-        const uint32_t w_base = smem_u32(wring + ws * W_STAGE);
+        const uint32_t a_base = smem_u32(planes + s * 3 * T6_PLANE);
+        for (int j = 0; j < nj; ++j, ++wit) {
+          const int ws = wit % WS;
+          mbar_wait(&w_full[ws], (wit / WS) & 1);
+          tc_fence_after();
+          const uint32_t w_base = smem_u32(wring + ws * W_STAGE);
 #pragma unroll
-        for (int t = 0; t < 6; ++t) {
-          const uint64_t da = make_smem_desc(a_base + pa[t] * T6_PLANE);
-          const uint64_t dw = make_smem_desc(w_base + pw[t] * (BN * T6_BK * 2));
-          const int set = t < 5 ? 0 : 1 + kb % pm;
-          const bool first = t < 5 ? (kb == 0 && t == 0) : (kb < pm);
+          for (int t = 0; t < 6; ++t) {
+            const uint64_t da = make_smem_desc(a_base + pa[t] * T6_PLANE);
+            const uint64_t dw = make_smem_desc(w_base + pw[t] * (BN * T6_BK * 2));
+            const int set = t < 5 ? 0 : 1 + kb % pm;
+            const bool first = t < 5 ? (kb == 0 && t == 0) : (kb < pm);
 #pragma unroll
-          for (int k = 0; k < T6_BK / 16; ++k)
-            umma_bf16(tmem_base + set * acc_stride + j * BN, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc,
-                      (first && k == 0) ? 0u : 1u);
+            for (int k = 0; k < T6_BK / 16; ++k)
+              umma_bf16(acc_base + set * acc_stride + j * BN, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc,
+                        (first && k == 0) ? 0u : 1u);
+          }
+          umma_commit(&w_empty[ws]);
         }
-        umma_commit(&w_empty[ws]);
+        umma_commit(&pl_empty[s]);
       }
-      umma_commit(&pl_empty[s]);
+      umma_commit(&acc_full[buf]);
     }
-    umma_commit(accum_bar);
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     // ---------------- converters: staging f32 -> three swizzled bf16 operand tiles ----------------
     const int cw = warp - 4;
     const int r = (cw & 3) * 32 + lane;      // tile row
     const int half = cw >> 2;                // which 32-wide half of the k-block
     const int sw = r & 7;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb & 1;
-      const uint32_t ph = (kb >> 1) & 1;
-      const bool have = (p.K - kb * T6_BK > 32) || half == 0;
-      float4 v[8];
-      mbar_wait(&stg_full[s], ph);
-      if (have) {
-        const uint8_t* src = stg + s * T6_STG + half * T6_STG_SUB + r * 128;
+    int kit = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb, ++kit) {
+        const int s = kit & 1;
+        const uint32_t ph = (kit >> 1) & 1;
+        const bool have = (p.K - kb * T6_BK > 32) || half == 0;
+        float4 v[8];
+        mbar_wait(&stg_full[s], ph);
+        if (have) {
+          const uint8_t* src = stg + s * T6_STG + half * T6_STG_SUB + r * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(src + ((c ^ sw) << 4));
-      } else {
+          for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(src + ((c ^ sw) << 4));
+        } else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c = 0; c < 8; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stg_empty[s]);      // staging slot may be refilled
+        mbar_wait(&pl_empty[s], ph ^ 1);                 // MMAs that read this plane buffer are done
+        uint8_t* dst = planes + s * 3 * T6_PLANE + r * 128;
+        // Exact 3-way split by TRUNCATION: b1 = top 16 bits of x, r1 = x - b1 (exact), b2 = top 16 bits of
+        // r1, r2 = r1 - b2 (exact), b3 = top 16 bits of r2 (r2 has <= 8 significant bits left, so b3 = r2).
+        // No F2F conversions: one PRMT packs the upper halves of two floats into a bf16x2.
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float4 x0 = v[2 * cc], x1 = v[2 * cc + 1];
+          const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          uint32_t p1[4], p2[4], p3[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a0 = xs[2 * e], a1 = xs[2 * e + 1];
+            const uint32_t u0 = __float_as_uint(a0), u1 = __float_as_uint(a1);
+            p1[e] = __byte_perm(u0, u1, 0x7632);
+            const float r0 = a0 - __uint_as_float(u0 & 0xffff0000u), r1 = a1 - __uint_as_float(u1 & 0xffff0000u);
+            const uint32_t v0 = __float_as_uint(r0), v1 = __float_as_uint(r1);
+            p2[e] = __byte_perm(v0, v1, 0x7632);
+            const float s0 = r0 - __uint_as_float(v0 & 0xffff0000u), s1 = r1 - __uint_as_float(v1 & 0xffff0000u);
+            p3[e] = __byte_perm(__float_as_uint(s0), __float_as_uint(s1), 0x7632);
+          }
+          const int chunk = ((half * 4 + cc) ^ sw) << 4;
+          *reinterpret_cast<uint4*>(dst + chunk) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+          *reinterpret_cast<uint4*>(dst + T6_PLANE + chunk) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+          *reinterpret_cast<uint4*>(dst + 2 * T6_PLANE + chunk) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
+        }
+        fence_proxy_async();      // make the generic-proxy stores visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pl_full[s]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&stg_empty[s]);      // staging slot may be refilled
-      mbar_wait(&pl_empty[s], ph ^ 1);                 // MMAs that read this plane buffer are done
-      uint8_t* dst = planes + s * 3 * T6_PLANE + r * 128;
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const float4 x0 = v[2 * cc], x1 = v[2 * cc + 1];
-        __nv_bfloat16 a[8], b[8], c3[8];
-        split3(x0.x, a[0], b[0], c3[0]);
-        split3(x0.y, a[1], b[1], c3[1]);
-        split3(x0.z, a[2], b[2], c3[2]);
-        split3(x0.w, a[3], b[3], c3[3]);
-        split3(x1.x, a[4], b[4], c3[4]);
-        split3(x1.y, a[5], b[5], c3[5]);
-        split3(x1.z, a[6], b[6], c3[6]);
-        split3(x1.w, a[7], b[7], c3[7]);
-        const int chunk = ((half * 4 + cc) ^ sw) << 4;
-        *reinterpret_cast<uint4*>(dst + chunk) =
-            make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7]));
-        *reinterpret_cast<uint4*>(dst + T6_PLANE + chunk) =
-            make_uint4(pack2(b[0], b[1]), pack2(b[2], b[3]), pack2(b[4], b[5]), pack2(b[6], b[7]));
-        *reinterpret_cast<uint4*>(dst + 2 * T6_PLANE + chunk) =
-            make_uint4(pack2(c3[0], c3[1]), pack2(c3[2], c3[3]), pack2(c3[4], c3[5]), pack2(c3[6], c3[7]));
-      }
-      fence_proxy_async();      // make the generic-proxy stores visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&pl_full[s]);
     }
-  }
-
-  // ---------------- epilogue: all twelve warps ----------------
-  __syncwarp();
-  mbar_wait(accum_bar, 0);
-  tc_fence_after();
-  const int quad = warp & 3, grp = warp >> 2;
-  const int r = quad * 32 + lane;
-  const int bl = r / p.t_sub, tl = r - bl * p.t_sub;
-  const int b = b0 + bl, t = t0 + tl;
-  const bool row_ok = r < rows_box && b < p.B && t < p.T_out;
-  const int m = b * p.T_out + t;
-  const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-  const float* res_row = (p.res && row_ok) ? p.res + p.r_map.off(m) : nullptr;
-  float* raw_row = (p.out_raw && row_ok) ? p.out_raw + p.o_map.off(m) : nullptr;
-  float* act_row = (p.out_act && row_ok) ? p.out_act + p.e_map.off(m) : nullptr;
-  const int n_chunks = nj * BN / 32;
+  } else if (warp >= 12) {
+    // ---------------- epilogue warps: two per TMEM lane quadrant ----------------
+    // A thread owns one TMEM lane = one output row, so a direct store would scatter 16-byte pieces over
+    // 32 rows per instruction; each warp transposes its 32x32 chunk through shared memory so that
+    // consecutive lanes write consecutive columns of one row (and reads the residual the same way).
+    // The two warps of a quadrant take alternate chunks; with a single chunk they split its rows.
+    const int ew = warp - 12;
+    const int quad = warp & 3, sib = ew >> 2;     // sibling index 0/1 within the quadrant
+    float* scratch = scratch_all + ew * (32 * 17);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    int li = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+      const int mt = tile / p.n_groups;
+      const int t0 = (mt % p.t_tiles) * p.t_sub, b0 = (mt / p.t_tiles) * p.b_sub;
+      const int n0 = (tile % p.n_groups) * p.nj * BN;
+      const int nj = min(p.nj, (p.N - n0 + BN - 1) / BN);
+      const int r = quad * 32 + lane;
+      const int bl = r / p.t_sub, tl = r - bl * p.t_sub;
+      const int b = b0 + bl, t = t0 + tl;
+      const uint32_t row_ok = (r < rows_box && b < p.B && t < p.T_out) ? 1u : 0u;
+      const int m = row_ok ? b * p.T_out + t : 0;
+      const uint32_t res_off = p.res ? (uint32_t)p.r_map.off(m) : 0u;
+      const uint32_t raw_off = p.out_raw ? (uint32_t)p.o_map.off(m) : 0u;
+      const uint32_t act_off = p.out_act ? (uint32_t)p.e_map.off(m) : 0u;
+      const uint32_t ok_mask = __ballot_sync(0xffffffffu, row_ok);
+      const int buf = li & 1;
+      mbar_wait(&acc_full[buf], (li >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc_addr = lane_addr + buf * buf_stride;
+      const int n_chunks = nj * BN / 32;
+      const bool split_rows = n_chunks == 1;       // both siblings work on chunk 0, half the rows each
+      const int rr0 = split_rows ? sib * 16 : 0, rr1 = split_rows ? rr0 + 16 : 32;
+      const int hrow = lane >> 4, cs = lane & 15;  // half-warp per row: 16 lanes x 4 B = 64 contiguous bytes
 #pragma unroll 1
-  for (int c = grp; c < n_chunks; c += 3) {
-    float v[32];
-    tmem_ld32(lane_addr + c * 32, v);
-    for (int a = 1; a <= pm; ++a) {
-      float u[32];
-      tmem_ld32(lane_addr + a * acc_stride + c * 32, u);
+      for (int c = split_rows ? 0 : sib; c < n_chunks; c += split_rows ? 1 : 2) {
+        float v[32];
+        tmem_ld32(acc_addr + c * 32, v);
+        for (int a = 1; a <= pm; ++a) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += u[i];
-    }
-    const int n = n0 + c * 32;
-    if (!row_ok || n >= p.N) continue;
+          for (int h = 0; h < 2; ++h) {
+            float u[16];
+            tmem_ld16(acc_addr + a * acc_stride + c * 32 + h * 16, u);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float x = v[i];
-      if (p.bias) x = p.neg ? __ldg(p.bias + n + i) - x : x + __ldg(p.bias + n + i);
-      if (p.act == 1) x = gelu_erf(x);
-      if (p.scale) x *= __ldg(p.scale + n + i);
-      v[i] = x;
-    }
-    if (res_row) {
+            for (int i = 0; i < 16; ++i) v[h * 16 + i] += u[i];
+          }
+        }
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 q = *reinterpret_cast<const float4*>(res_row + n + i);
-        v[i] += q.x, v[i + 1] += q.y, v[i + 2] += q.z, v[i + 3] += q.w;
+        for (int h = 0; h < 2; ++h) {
+          // 16 columns at a time through a [32][17] scratch tile
+#pragma unroll
+          for (int i = 0; i < 16; ++i) scratch[lane * 17 + i] = v[h * 16 + i];
+          __syncwarp();
+          const int col = n0 + c * 32 + h * 16 + cs;
+          const bool col_ok = col < p.N;
+          const float bias_l = (p.bias && col_ok) ? __ldg(p.bias + col) : 0.f;
+          const float scale_l = (p.scale && col_ok) ? __ldg(p.scale + col) : 1.f;
+#pragma unroll 1
+          for (int g0 = rr0; g0 < rr1; g0 += 16) {
+            float rres[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int rr = g0 + 2 * q + hrow;
+              const uint32_t ro = __shfl_sync(0xffffffffu, res_off, rr);
+              rres[q] = (p.res && col_ok && ((ok_mask >> rr) & 1u)) ? __ldg(p.res + ro + col) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int rr = g0 + 2 * q + hrow;
+              const uint32_t wo = __shfl_sync(0xffffffffu, raw_off, rr);
+              const uint32_t ao = __shfl_sync(0xffffffffu, act_off, rr);
+              if (!col_ok || !((ok_mask >> rr) & 1u)) continue;
+              float x = scratch[rr * 17 + cs];
+              if (p.bias) x = p.neg ? bias_l - x : x + bias_l;
+              if (p.act == 1) x = gelu_erf(x);
+              x = x * scale_l + rres[q];
+              if (p.out_raw) p.out_raw[wo + col] = x;
+              if (p.out_act) p.out_act[ao + col] = elu_ref(x);
+            }
+          }
+          __syncwarp();
+        }
       }
-    }
-    if (raw_row) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        *reinterpret_cast<float4*>(raw_row + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    }
-    if (act_row) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        *reinterpret_cast<float4*>(act_row + n + i) = make_float4(elu1(v[i]), elu1(v[i + 1]), elu1(v[i + 2]), elu1(v[i + 3]));
+      // this warp is done reading the TMEM buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 // ================================================================================================
@@ -404,9 +464,11 @@ template <int BN>
 struct T6Cfg {
   static constexpr int W_STAGE = 3 * BN * T6_BK * 2;
   static constexpr int FIXED = 2 * T6_STG + 2 * 3 * T6_PLANE;             // 160 KB
-  static constexpr int WS_RAW = (212 * 1024 - FIXED) / W_STAGE;
+  static constexpr int WS_RAW = (209 * 1024 - FIXED) / W_STAGE;
   static constexpr int WS = WS_RAW > 4 ? 4 : WS_RAW;
-  static constexpr int SMEM = FIXED + WS * W_STAGE + (9 + 2 * WS) * 8 + 16 + 1024;
+  static constexpr int SCRATCH = T6_EPI_WARPS * 32 * 17 * 4;
+  static constexpr int SMEM = FIXED + WS * W_STAGE + SCRATCH + (12 + 2 * WS) * 8 + 16 + 1024;
+  static_assert(SMEM <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static_assert(WS >= 2, "need at least two W stages");
 };
 
@@ -422,9 +484,12 @@ static void launch6(const Tc6Gemm& g, cudaStream_t st) {
   Tc6Params p;
   p.K = g.K, p.N = g.N, p.T_out = g.T_out, p.B = g.B, p.t_sub = g.t_sub, p.b_sub = g.b_sub;
   p.t_tiles = ceil_div(g.T_out, g.t_sub), p.nj = g.nj, p.pm = g.pm;
+  p.m_tiles = p.t_tiles * ceil_div(g.B, g.b_sub);
+  p.n_groups = ceil_div(g.N, g.nj * BN);
   p.bias = g.ep.bias, p.neg = g.ep.neg, p.scale = g.ep.scale, p.res = g.ep.res, p.r_map = g.ep.r_map, p.act = g.ep.act;
   p.out_raw = g.ep.out_raw, p.o_map = g.ep.o_map, p.out_act = g.ep.out_act, p.e_map = g.ep.e_map;
-  dim3 grid(p.t_tiles * ceil_div(g.B, g.b_sub), ceil_div(g.N, g.nj * BN));
+  const long long tiles = (long long)p.m_tiles * p.n_groups;
+  const int grid = (int)std::min<long long>(tiles, 148);
   kern<<<grid, T6_THREADS, C::SMEM, st>>>(g.map_a, g.map_w, p);
   check_launch("tc6_gemm");
 }
@@ -472,6 +537,11 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes)
   DSM_CHECK(tc6_supported(g), DSM_ERR_UNSUPPORTED, "tc6_gemm: unsupported problem M=%d N=%d K=%d", g.M, g.N, g.K);
   t.ep = g;
   t.K = g.K, t.N = g.N, t.T_out = g.a_map.T, t.B = g.M / g.a_map.T;
+  // the epilogue keeps row offsets in 32 bits
+  for (const RowMap* rm : {&g.r_map, &g.o_map, &g.e_map}) {
+    const long long extent = rm->off(g.M - 1) + g.N;
+    DSM_CHECK(extent < (1LL << 32), DSM_ERR_UNSUPPORTED, "tc6_gemm: output extent %lld exceeds 32-bit element offsets", extent);
+  }
   // rows of a tile: a run of time steps of one stream, or whole (short) streams side by side
   if (t.T_out >= T6_BM || T6_BM % t.T_out != 0) t.t_sub = std::min(t.T_out, T6_BM), t.b_sub = 1;
   else t.t_sub = t.T_out, t.b_sub = T6_BM / t.T_out;
@@ -479,11 +549,12 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes)
   const long long m_tiles = (long long)ceil_div(t.T_out, t.t_sub) * ceil_div(t.B, t.b_sub);
   const int n_sub = ceil_div(g.N, t.bn);
   // column sub-tiles per CTA: as many as TMEM holds (512 columns) while the grid still covers the SMs
-  // (TMEM: 512 columns shared by the correction accumulator and >= 1 main accumulator => <= 256 columns)
-  int nj = std::min(n_sub, 256 / t.bn);
+  // (TMEM: two tile buffers of 256 columns, each shared by the correction accumulator and >= 1 main
+  // accumulator => at most 128 output columns per tile)
+  int nj = std::min(n_sub, 128 / t.bn);
   while (nj > 1 && m_tiles * ceil_div(n_sub, nj) < 148) nj = (nj + 1) / 2;
   t.nj = nj;
-  t.pm = std::max(1, std::min(7, 512 / (nj * t.bn) - 1));
+  t.pm = std::max(1, std::min(7, 256 / (nj * t.bn) - 1));
   // A: f32 [B][T_out][K] window view, box 32 x t_sub x b_sub
   {
     cuuint64_t gdim[3] = {(cuuint64_t)g.K, (cuuint64_t)t.T_out, (cuuint64_t)t.B};
