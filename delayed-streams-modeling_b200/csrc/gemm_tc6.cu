@@ -135,7 +135,8 @@ constexpr int T6_STG_SUB = T6_BM * 32 * 4;       // one staging sub-tile: 128 ro
 constexpr int T6_STG = 2 * T6_STG_SUB;           // 32 KB per k-block
 constexpr int T6_PLANE = T6_BM * T6_BK * 2;      // 16 KB per bf16 plane tile
 constexpr int T6_EPI_WARPS = 8;      // two per TMEM lane quadrant
-constexpr int T6_THREADS = (12 + T6_EPI_WARPS) * 32;
+constexpr int T6_CVT_WARPS = 4;      // one converter thread per tile row
+constexpr int T6_THREADS = (4 + T6_CVT_WARPS + T6_EPI_WARPS) * 32;
 
 }  // namespace
 
@@ -163,16 +164,17 @@ struct Tc6Params {
 // Persistent: gridDim.x CTAs (<= one per SM) walk the tiles; TMEM holds two accumulator buffers so the
 // epilogue warps drain tile i while the producers / converters / MMA issuer are already on tile i+1.
 template <int BN, int WS>
-__global__ void __launch_bounds__(T6_THREADS, 1)
+__global__ void __maxnreg__(96)   // 512 x 96 registers leave room for two attention CTAs on the same SM
 tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Tc6Params p) {
   constexpr int W_STAGE = 3 * BN * T6_BK * 2;   // three bf16 planes of a BN x 64 tile
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzle atoms need a 1024-byte aligned base
   uint8_t* stg = smem;                           // [2][T6_STG]
   uint8_t* planes = stg + 2 * T6_STG;            // [2][3][T6_PLANE]
   uint8_t* wring = planes + 2 * 3 * T6_PLANE;    // [WS][W_STAGE]
-  float* scratch_all = reinterpret_cast<float*>(wring + WS * W_STAGE);   // [epilogue warps][32][17]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + T6_EPI_WARPS * 32 * 17);
+  float* scratch_all = reinterpret_cast<float*>(wring + WS * W_STAGE);   // [epilogue warps][32][9]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + T6_EPI_WARPS * 32 * 9);
   uint64_t* stg_full = bars;             // [2]
   uint64_t* stg_empty = bars + 2;        // [2]
   uint64_t* pl_full = bars + 4;          // [2]
@@ -198,8 +200,8 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&stg_full[s], 1);
-      mbar_init(&stg_empty[s], 8);
-      mbar_init(&pl_full[s], 8);
+      mbar_init(&stg_empty[s], T6_CVT_WARPS);
+      mbar_init(&pl_full[s], T6_CVT_WARPS);
       mbar_init(&pl_empty[s], 1);
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], T6_EPI_WARPS);
@@ -292,27 +294,25 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
       umma_commit(&acc_full[buf]);
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 4 && warp < 4 + T6_CVT_WARPS) {
     // ---------------- converters: staging f32 -> three swizzled bf16 operand tiles ----------------
-    const int cw = warp - 4;
-    const int r = (cw & 3) * 32 + lane;      // tile row
-    const int half = cw >> 2;                // which 32-wide half of the k-block
+    const int r = (warp - 4) * 32 + lane;    // tile row
     const int sw = r & 7;
     int kit = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb, ++kit) {
         const int s = kit & 1;
         const uint32_t ph = (kit >> 1) & 1;
-        const bool have = (p.K - kb * T6_BK > 32) || half == 0;
-        float4 v[8];
+        const bool have2 = p.K - kb * T6_BK > 32;      // second 32-wide half present
+        float4 v[16];
         mbar_wait(&stg_full[s], ph);
-        if (have) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
           const uint8_t* src = stg + s * T6_STG + half * T6_STG_SUB + r * 128;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(src + ((c ^ sw) << 4));
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c = 0; c < 8; ++c)
+            v[half * 8 + c] = (half == 0 || have2) ? *reinterpret_cast<const float4*>(src + ((c ^ sw) << 4))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&stg_empty[s]);      // staging slot may be refilled
@@ -322,7 +322,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // r1, r2 = r1 - b2 (exact), b3 = top 16 bits of r2 (r2 has <= 8 significant bits left, so b3 = r2).
         // No F2F conversions: one PRMT packs the upper halves of two floats into a bf16x2.
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < 8; ++cc) {
           const float4 x0 = v[2 * cc], x1 = v[2 * cc + 1];
           const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
           uint32_t p1[4], p2[4], p3[4];
@@ -337,7 +337,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const float s0 = r0 - __uint_as_float(v0 & 0xffff0000u), s1 = r1 - __uint_as_float(v1 & 0xffff0000u);
             p3[e] = __byte_perm(__float_as_uint(s0), __float_as_uint(s1), 0x7632);
           }
-          const int chunk = ((half * 4 + cc) ^ sw) << 4;
+          const int chunk = (cc ^ sw) << 4;
           *reinterpret_cast<uint4*>(dst + chunk) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
           *reinterpret_cast<uint4*>(dst + T6_PLANE + chunk) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
           *reinterpret_cast<uint4*>(dst + 2 * T6_PLANE + chunk) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
@@ -347,15 +347,15 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (lane == 0) mbar_arrive(&pl_full[s]);
       }
     }
-  } else if (warp >= 12) {
+  } else if (warp >= 4 + T6_CVT_WARPS) {
     // ---------------- epilogue warps: two per TMEM lane quadrant ----------------
     // A thread owns one TMEM lane = one output row, so a direct store would scatter 16-byte pieces over
     // 32 rows per instruction; each warp transposes its 32x32 chunk through shared memory so that
     // consecutive lanes write consecutive columns of one row (and reads the residual the same way).
     // The two warps of a quadrant take alternate chunks; with a single chunk they split its rows.
-    const int ew = warp - 12;
+    const int ew = warp - (4 + T6_CVT_WARPS);
     const int quad = warp & 3, sib = ew >> 2;     // sibling index 0/1 within the quadrant
-    float* scratch = scratch_all + ew * (32 * 17);
+    float* scratch = scratch_all + ew * (32 * 9);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     int li = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
@@ -379,7 +379,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int n_chunks = nj * BN / 32;
       const bool split_rows = n_chunks == 1;       // both siblings work on chunk 0, half the rows each
       const int rr0 = split_rows ? sib * 16 : 0, rr1 = split_rows ? rr0 + 16 : 32;
-      const int hrow = lane >> 4, cs = lane & 15;  // half-warp per row: 16 lanes x 4 B = 64 contiguous bytes
+      const int qrow = lane >> 3, cs = lane & 7;   // 8 lanes per row: 32 contiguous bytes (one sector)
 #pragma unroll 1
       for (int c = split_rows ? 0 : sib; c < n_chunks; c += split_rows ? 1 : 2) {
         float v[32];
@@ -394,37 +394,35 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          // 16 columns at a time through a [32][17] scratch tile
+        for (int h = 0; h < 4; ++h) {
+          // 8 columns at a time through a [32][9] scratch tile
 #pragma unroll
-          for (int i = 0; i < 16; ++i) scratch[lane * 17 + i] = v[h * 16 + i];
+          for (int i = 0; i < 8; ++i) scratch[lane * 9 + i] = v[h * 8 + i];
           __syncwarp();
-          const int col = n0 + c * 32 + h * 16 + cs;
+          const int col = n0 + c * 32 + h * 8 + cs;
           const bool col_ok = col < p.N;
           const float bias_l = (p.bias && col_ok) ? __ldg(p.bias + col) : 0.f;
           const float scale_l = (p.scale && col_ok) ? __ldg(p.scale + col) : 1.f;
-#pragma unroll 1
-          for (int g0 = rr0; g0 < rr1; g0 += 16) {
-            float rres[8];
+          float rres[8];
+          const int nq = (rr1 - rr0) / 4;          // 4 or 8 row groups of 4 rows
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int rr = g0 + 2 * q + hrow;
-              const uint32_t ro = __shfl_sync(0xffffffffu, res_off, rr);
-              rres[q] = (p.res && col_ok && ((ok_mask >> rr) & 1u)) ? __ldg(p.res + ro + col) : 0.f;
-            }
+          for (int q = 0; q < 8; ++q) {
+            const int rr = rr0 + 4 * q + qrow;
+            const uint32_t ro = __shfl_sync(0xffffffffu, res_off, rr & 31);
+            rres[q] = (q < nq && p.res && col_ok && ((ok_mask >> rr) & 1u)) ? __ldg(p.res + ro + col) : 0.f;
+          }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int rr = g0 + 2 * q + hrow;
-              const uint32_t wo = __shfl_sync(0xffffffffu, raw_off, rr);
-              const uint32_t ao = __shfl_sync(0xffffffffu, act_off, rr);
-              if (!col_ok || !((ok_mask >> rr) & 1u)) continue;
-              float x = scratch[rr * 17 + cs];
-              if (p.bias) x = p.neg ? bias_l - x : x + bias_l;
-              if (p.act == 1) x = gelu_erf(x);
-              x = x * scale_l + rres[q];
-              if (p.out_raw) p.out_raw[wo + col] = x;
-              if (p.out_act) p.out_act[ao + col] = elu_ref(x);
-            }
+          for (int q = 0; q < 8; ++q) {
+            const int rr = rr0 + 4 * q + qrow;
+            const uint32_t wo = __shfl_sync(0xffffffffu, raw_off, rr & 31);
+            const uint32_t ao = __shfl_sync(0xffffffffu, act_off, rr & 31);
+            if (q >= nq || !col_ok || !((ok_mask >> rr) & 1u)) continue;
+            float x = scratch[rr * 9 + cs];
+            if (p.bias) x = p.neg ? bias_l - x : x + bias_l;
+            if (p.act == 1) x = gelu_erf(x);
+            x = x * scale_l + rres[q];
+            if (p.out_raw) p.out_raw[wo + col] = x;
+            if (p.out_act) p.out_act[ao + col] = elu_ref(x);
           }
           __syncwarp();
         }
@@ -466,8 +464,8 @@ struct T6Cfg {
   static constexpr int FIXED = 2 * T6_STG + 2 * 3 * T6_PLANE;             // 160 KB
   static constexpr int WS_RAW = (209 * 1024 - FIXED) / W_STAGE;
   static constexpr int WS = WS_RAW > 4 ? 4 : WS_RAW;
-  static constexpr int SCRATCH = T6_EPI_WARPS * 32 * 17 * 4;
-  static constexpr int SMEM = FIXED + WS * W_STAGE + SCRATCH + (12 + 2 * WS) * 8 + 16 + 1024;
+  static constexpr int SCRATCH = T6_EPI_WARPS * 32 * 9 * 4;
+  static constexpr int SMEM = FIXED + WS * W_STAGE + SCRATCH + (12 + 2 * WS) * 8 + 16;
   static_assert(SMEM <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static_assert(WS >= 2, "need at least two W stages");
 };

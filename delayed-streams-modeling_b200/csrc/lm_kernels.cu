@@ -1,6 +1,8 @@
 // Hand-written kernels of the delayed-streams LM step that are not GEMMs: embedding sum, RMSNorm,
 // RoPE + ring scatter, single-query ring attention (bf16 KV, f32 math), SiLU gate, greedy argmax,
 // VAD extra heads, and the ASR token feed / commit.
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace dsm {
@@ -146,8 +148,8 @@ __global__ void __launch_bounds__(128) lm_attention_kernel(const __nv_bfloat16* 
   constexpr int KPW = 32 / LPK;       // keys per warp-load
   constexpr int NW = 4;
   extern __shared__ float sm[];
-  float* sc = sm;                     // [context]
-  float* red = sm + context;          // [NW][D]
+  float* sc = sm;                     // [context] scores, then reused as [NW][D] partial outputs
+  float* red = sm;
   __shared__ float s_red[NW];
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(128) lm_attention_kernel(const __nv_bfloat16* 
 #pragma unroll
     for (int o = LPK; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
   }
+  __syncthreads();                    // every warp is done reading the probabilities in sc[]
   if (sub == 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[warp * D + c8 * 8 + i] = acc[i];
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(128) lm_attention_kernel(const __nv_bfloat16* 
 void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint8_t* mask, int B, int H, int D,
                          int context, const __nv_bfloat16* k_ring, const __nv_bfloat16* v_ring, __nv_bfloat16* out,
                          cudaStream_t st) {
-  size_t smem = (size_t)(context + 4 * D) * sizeof(float);
+  size_t smem = (size_t)std::max(context, 4 * D) * sizeof(float);
   if (D == 128)
     lm_attention_kernel<128, 8><<<B * H, 128, smem, st>>>(q, rs, mask, H, context, k_ring, v_ring, out);
   else if (D == 64)

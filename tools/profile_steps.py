@@ -21,7 +21,7 @@ ap.add_argument("--streams", type=int, default=256)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--eager", action="store_true")
 ap.add_argument("--model", default="1b")
-ap.add_argument("--workload", default="asr", choices=["asr", "mimi", "decode"])
+ap.add_argument("--workload", default="asr", choices=["asr", "mimi", "decode", "lm"])
 a = ap.parse_args()
 if a.eager:
     api.set_graphs(False)
@@ -38,11 +38,28 @@ if a.workload == "asr":
     for i in range(a.steps):
         asr.step_pcm(frame(audio, i), None, want_messages=False)
         print("step", i, "ms", asr.last_step_ms())
-elif a.workload == "mimi":
-    mimi = api.Mimi(mspec, None, B, decoder=False)
+elif a.workload == "lm":
+    import time
+    lm = api.LmModel(lspec, None, B)
+    asr = api.AsrState(None, lm)
+    lm.debug_set_position(2000)
+    codes = np.random.default_rng(7).integers(0, 2048, (B, 32)).astype(np.uint32)
     for i in range(a.steps):
-        mimi.encode_step(frame(audio, i), None)
-    print("ok")
+        t0 = time.perf_counter()
+        asr.step_tokens(codes, None, want_messages=False)
+        print("lm step", i, "wall ms", (time.perf_counter() - t0) * 1e3, "device ms", asr.last_step_ms()[0])
+elif a.workload == "mimi":
+    import time
+    import torch
+    mimi = api.Mimi(mspec, None, B, decoder=False)
+    pcm = [torch.from_numpy(frame(audio, i)).cuda() for i in range(a.steps)]
+    out = torch.empty((B, 32), dtype=torch.int32, device="cuda")
+    for i in range(a.steps):
+        mimi.synchronize()
+        t0 = time.perf_counter()
+        mimi.encode_step(pcm[i], None, out=out)
+        mimi.synchronize()
+        print("mimi step", i, "wall ms", (time.perf_counter() - t0) * 1e3)
 else:
     mimi = api.Mimi(mspec, None, B, encoder=False, decoder=True)
     codes = np.random.default_rng(7).integers(0, 2048, (B, 32)).astype(np.uint32)
