@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """Benchmark of the batched streaming-STT hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload asr|mimi]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload asr|asr-2.6b|mimi|decode] [--streams B]
 
 Workload (config.workload): stt-1b-en_fr full ASR step -- Mimi encode_step of the current 80 ms frame
 plus the delayed-streams LM step on the previous frame's codes, greedy text token -- for 256
-independent streams per GPU (BASELINE.json configs[2]; configs[1] is the codec alone and is available
-as --workload mimi).  One "step" = one frame for every stream of the batch; metric = stream-frames/s
+independent streams per GPU (BASELINE.json configs[2]).  The other single-GPU configurations are
+available as --workload mimi (configs[1]: codec encode alone, 64 streams), asr-2.6b (configs[3]:
+stt-2.6b-en, 128 streams) and decode (configs[4]: Mimi decode_step, 64 streams).  One "step" = one frame for every stream of the batch; metric = stream-frames/s
 over all GPUs.  Synthetic 24 kHz audio (SURVEY.md 8(d) generator), seeded random-init weights of the
 named architecture (no checkpoints offline).
 
@@ -132,13 +134,20 @@ def oracle_throughput(workload: str, streams: int, steps: int, warmup: int):
     def rand_like(shapes):
         return {k: torch.randn(*s, generator=g) * (1.0 / max(s[-1], 1)) ** 0.5 for k, s in shapes.items()}
 
-    mspec, lspec = MimiSpec(), stt_1b_en_fr()
+    from dsm_b200.spec import stt_2_6b_en
+    mspec = MimiSpec()
+    lspec = stt_2_6b_en() if workload == "asr-2.6b" else stt_1b_en_fr()
     from dsm_b200.weights import mimi_weights
-    mimi = Mimi(mspec, mimi_weights(mspec, seed=0, decoder=False), streams, decoder=False)
+    mimi = Mimi(mspec, mimi_weights(mspec, seed=0, decoder=workload == "decode"), streams, decoder=workload == "decode")
     audio = synth_audio(streams, warmup + steps)
     if workload == "mimi":
         def step(i):
             mimi.encode_step(torch.from_numpy(frame(audio, i)).unsqueeze(1), None)
+    elif workload == "decode":
+        codes = torch.randint(0, 2048, (streams, 32, 1), generator=g)
+
+        def step(i):
+            mimi.decode_step(codes, None)
     else:
         d, h = lspec.d_model, lspec.hidden
         shapes = {"text_emb.weight": (lspec.text_in_vocab_size, d), "out_norm.alpha": (1, 1, d),
@@ -186,12 +195,18 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+WORKLOADS = {
+    "asr": ("stt-1b-en_fr full ASR step (Mimi encode_step + delayed-streams LM step, greedy token)", 256),
+    "asr-2.6b": ("stt-2.6b-en full ASR step (Mimi encode_step + delayed-streams LM step, greedy token)", 128),
+    "mimi": ("Mimi streaming encode_step + RVQ only (codec kernels in isolation)", 64),
+    "decode": ("Mimi streaming decode_step (RVQ dequant + conv-transpose SEANet decoder)", 64),
+}
+
+
 def workload_config(args):
-    name = ("stt-1b-en_fr full ASR step (Mimi encode_step + delayed-streams LM step, greedy token)"
-            if args.workload == "asr" else "Mimi streaming encode_step + RVQ only (codec kernels in isolation)")
-    return {"workload": name, "streams_per_gpu": args.streams, "frame_samples": FRAME, "n_q": 32,
+    return {"workload": WORKLOADS[args.workload][0], "streams_per_gpu": args.streams, "frame_samples": FRAME, "n_q": 32,
             "parallelism": f"streams sharded over {args.gpus} GPU(s), no step-path collective",
-            "l2": "per-step working set (KV rings, 25 GB at 256 streams) far exceeds the 126 MB L2",
+            "l2": "per-step working set (KV rings: 25 GB LM + 2 GB codec at 256 streams) far exceeds the 126 MB L2",
             "ring_prefill_steps": args.prefill}
 
 
@@ -220,10 +235,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from dsm_b200.spec import stt_2_6b_en
     B = args.streams
-    mspec, lspec = MimiSpec(), stt_1b_en_fr()
-    mimi = api.Mimi(mspec, None, B, device=local, decoder=False)
-    if args.workload == "asr":
+    mspec = MimiSpec()
+    lspec = stt_2_6b_en() if args.workload == "asr-2.6b" else stt_1b_en_fr()
+    is_asr = args.workload.startswith("asr")
+    mimi = api.Mimi(mspec, None, B, device=local, encoder=args.workload != "decode", decoder=args.workload == "decode")
+    if is_asr:
         lm = api.LmModel(lspec, None, B, device=local)
         asr = api.AsrState(mimi, lm)
         stream_ptr = lm.stream()
@@ -238,12 +256,22 @@ def run_ours(args):
     dev_frames = [torch.from_numpy(frame(audio, i)).cuda() for i in range(n_audio)]
     host_frames = [torch.from_numpy(frame(audio, i)).pin_memory() for i in range(n_audio)]
     codes_dev = torch.empty((B, mspec.n_q), dtype=torch.int32, device="cuda")
+    if args.workload == "decode":
+        # config 5 input: codes ~ U[0, 2048), seed 7; device- and host-resident copies
+        rng = np.random.default_rng(7 + rank)
+        code_sets = [rng.integers(0, 2048, (B, mspec.n_q)).astype(np.int32) for _ in range(n_audio)]
+        dev_frames = [torch.from_numpy(c).cuda() for c in code_sets]
+        host_frames = [torch.from_numpy(c).pin_memory() for c in code_sets]
+        pcm_dev = torch.empty((B, FRAME), dtype=torch.float32, device="cuda")
+        pcm_host = torch.empty((B, FRAME), dtype=torch.float32).pin_memory()
 
     def step(i, src):
         if asr is not None:
             asr.step_pcm(src[i % n_audio], None, want_messages=False)
+        elif args.workload == "decode":
+            mimi.decode_step(src[i % n_audio], None, out=pcm_dev if src is dev_frames else pcm_host)
         else:
-            mimi.encode_step(src[i % n_audio], None, out=codes_dev)
+            mimi.encode_step(src[i % n_audio], None, out=codes_dev if src is dev_frames else None)
 
     def timed(n, src):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -274,6 +302,21 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel: single-query ring attention (LM), timed per launch ----
     roofline = None
+    steps_done = args.prefill + args.warmup + 2 * args.steps
+    if asr is None and rank == 0:
+        # codec-only workloads are tensor-pipe work: 0.468 (encode) / 0.441 (decode) GFLOP of f32 MACs per
+        # stream-frame, each f32 MAC costing six bf16 MMAs in the split-bf16 tcgen05 GEMM
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                tf = float(json.load(f)["bf16_tflops_sustained"])
+            src_tf = "measured (MEASURED_PEAKS.json bf16_tflops_sustained) / 6"
+        except Exception:
+            tf, src_tf = 1400.0, "fallback (B200_PROFILING.md 1.4 PFLOP/s sustained) / 6"
+        gflop = (0.441 if args.workload == "decode" else 0.468) * B
+        ach = gflop / (ms_dev / args.steps)           # GFLOP per ms = TFLOP/s
+        roofline = {"bound": "tensor", "kernel": "tc6_gemm_kernel (f32-accurate split-bf16 tcgen05 GEMMs of the step)",
+                    "achieved": ach, "peak": tf / 6.0, "unit": "TFLOP/s", "frac": ach / (tf / 6.0), "traffic": None,
+                    "peak_source": src_tf, "how": "f32 FLOPs of one step / CUDA-event step time (whole step, not one launch)"}
     if asr is not None and rank == 0:
         peak, peak_src = measured_peaks()
         api.set_graphs(False)
@@ -290,7 +333,8 @@ def run_ours(args):
         # algorithmic bytes per launch: K and V rings read once (ctx slots x head_dim bf16 per (stream, head)),
         # plus q in and the attention output out
         d = lspec.d_model
-        bytes_per_launch = B * lspec.num_heads * lspec.context * lspec.head_dim * 2 * 2 + 2 * B * d * 2
+        visible = min(steps_done, lspec.context)          # ring slots a query sees (full ring once wrapped)
+        bytes_per_launch = B * lspec.num_heads * visible * lspec.head_dim * 2 * 2 + 2 * B * d * 2
         avg_ms = ms_sum / max(n_launch, 1)
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
         step_ms = ms_dev / args.steps
@@ -318,7 +362,8 @@ def run_ours(args):
                 "config": workload_config(args),
                 "realtime_streams": value / 12.5,
                 "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                        "h2d_bytes_per_step": B * FRAME * 4 + B, "d2h_bytes_per_step": B * 4 + (16 * B if asr else B * 128)},
+                        "h2d_bytes_per_step": (B * 128 if args.workload == "decode" else B * FRAME * 4) + B, "d2h_bytes_per_step": (B * 4 + 4 * lspec.extra_heads_num * B) if asr else
+                        (B * FRAME * 4 if args.workload == "decode" else B * 128)},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -331,13 +376,15 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="asr", choices=["asr", "mimi"])
-    ap.add_argument("--streams", type=int, default=256, help="streams per GPU")
+    ap.add_argument("--workload", default="asr", choices=sorted(WORKLOADS))
+    ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's BASELINE batch)")
     ap.add_argument("--prefill", type=int, default=760, help="untimed steps that fill and wrap the KV rings")
     ap.add_argument("--ref-streams", type=int, default=8, help="streams of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.streams <= 0:
+        args.streams = WORKLOADS[args.workload][1]
     if args.impl == "reference":
         run_reference(args)
     else:

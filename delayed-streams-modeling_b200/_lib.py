@@ -57,6 +57,12 @@ class AsrMsgC(C.Structure):
                 ("tokens", C.POINTER(C.c_uint32)), ("time", C.c_double), ("prs", C.POINTER(C.c_float))]
 
 
+class SchedOutC(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("slot", C.c_int32), ("channel_id", C.c_uint64), ("step_idx", C.c_int32),
+                ("n_tokens", C.c_int32), ("tokens", C.POINTER(C.c_uint32)), ("time", C.c_double), ("n_prs", C.c_int32),
+                ("prs", C.POINTER(C.c_float)), ("marker_id", C.c_int64), ("buffered_pcm", C.c_int64)]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol the header declares
@@ -116,6 +122,19 @@ SIGNATURES = {
     "dsm_asr_delay_in_tokens": (C.c_int32, [_P]),
     "dsm_asr_last_logits": (C.c_int32, [_P, _P]),
     "dsm_asr_last_step_ms": (C.c_int32, [_P, C.POINTER(C.c_float * 3)]),
+    "dsm_sched_create": (C.c_int32, [_P, C.c_int32, C.POINTER(_P)]),
+    "dsm_sched_destroy": (None, [_P]),
+    "dsm_sched_open": (C.c_int32, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
+    "dsm_sched_close": (C.c_int32, [_P, C.c_int32]),
+    "dsm_sched_push_audio": (C.c_int32, [_P, C.c_int32, _P, C.c_int64]),
+    "dsm_sched_push_marker": (C.c_int32, [_P, C.c_int32, C.c_int64]),
+    "dsm_sched_tick": (C.c_int32, [_P, C.POINTER(C.c_int32)]),
+    "dsm_sched_out_count": (C.c_int32, [_P]),
+    "dsm_sched_out_get": (C.c_int32, [_P, C.c_int32, C.POINTER(SchedOutC)]),
+    "dsm_sched_free_slots": (C.c_int32, [_P]),
+    "dsm_sched_step_idx": (C.c_int64, [_P]),
+    "dsm_sched_last_mask": (C.POINTER(C.c_uint8), [_P]),
+    "dsm_sched_batch_pcm": (C.POINTER(C.c_float), [_P]),
 }
 
 

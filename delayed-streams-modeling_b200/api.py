@@ -288,6 +288,73 @@ class AsrState:
         check(self._lib.dsm_asr_reset_batch_idx(self._h, batch_idx))
 
 
+class BatchedAsr:
+    """Slot scheduler of moshi-server's ``BatchedAsr`` (batched_asr.rs:216-717) over ``dsm_sched_*``.
+    ``asr=None`` builds a dry scheduler (host logic only) with ``batch_size`` slots."""
+
+    KINDS = {0: "step", 1: "word", 2: "end_word", 3: "marker", 4: "ready"}
+
+    def __init__(self, asr: Optional[AsrState], batch_size: int = 0):
+        self._lib = _lib.load()
+        self.asr = asr
+        self._h = C.c_void_p()
+        check(self._lib.dsm_sched_create(asr._h if asr is not None else None, batch_size, C.byref(self._h)))
+        self.batch_size = asr.batch_size() if asr is not None else batch_size
+
+    def close_handle(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.dsm_sched_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close_handle
+
+    def open(self) -> Tuple[int, int]:
+        slot, cid = C.c_int32(-1), C.c_uint64(0)
+        check(self._lib.dsm_sched_open(self._h, C.byref(slot), C.byref(cid)))
+        return slot.value, cid.value
+
+    def close(self, slot: int):
+        check(self._lib.dsm_sched_close(self._h, slot))
+
+    def push_audio(self, slot: int, pcm):
+        a = np.ascontiguousarray(np.asarray(pcm, dtype=np.float32).reshape(-1))
+        check(self._lib.dsm_sched_push_audio(self._h, slot, ptr(a), a.size))
+
+    def push_marker(self, slot: int, marker_id: int):
+        check(self._lib.dsm_sched_push_marker(self._h, slot, marker_id))
+
+    def tick(self) -> Tuple[bool, List[dict]]:
+        stepped = C.c_int32(0)
+        check(self._lib.dsm_sched_tick(self._h, C.byref(stepped)))
+        outs = []
+        o = _lib.SchedOutC()
+        for i in range(self._lib.dsm_sched_out_count(self._h)):
+            check(self._lib.dsm_sched_out_get(self._h, i, C.byref(o)))
+            d = {"kind": self.KINDS[o.kind], "slot": o.slot, "channel_id": o.channel_id, "step_idx": o.step_idx}
+            if o.kind == 1:
+                d.update(tokens=[int(o.tokens[j]) for j in range(o.n_tokens)], start_time=o.time)
+            elif o.kind == 2:
+                d.update(stop_time=o.time)
+            elif o.kind == 0:
+                d.update(prs=[float(o.prs[j]) for j in range(o.n_prs)], buffered_pcm=o.buffered_pcm)
+            elif o.kind == 3:
+                d.update(marker_id=o.marker_id)
+            outs.append(d)
+        return bool(stepped.value), outs
+
+    def free_slots(self) -> int:
+        return self._lib.dsm_sched_free_slots(self._h)
+
+    def step_idx(self) -> int:
+        return self._lib.dsm_sched_step_idx(self._h)
+
+    def last_mask(self) -> np.ndarray:
+        return np.ctypeslib.as_array(self._lib.dsm_sched_last_mask(self._h), shape=(self.batch_size,)).copy()
+
+    def batch_pcm(self) -> np.ndarray:
+        return np.ctypeslib.as_array(self._lib.dsm_sched_batch_pcm(self._h), shape=(self.batch_size, FRAME_SIZE)).copy()
+
+
 def set_graphs(enabled: bool):
     _lib.load().dsm_set_graphs(int(enabled))
 

@@ -1,14 +1,9 @@
 // extern "C" boundary (include/dsm_b200.h): argument checks, exception -> status translation.
 #include <cstring>
 
-#include "lm.cuh"
-#include "mimi.cuh"
+#include "handles.cuh"
 
 using namespace dsm;
-
-struct dsm_mimi { MimiImpl* impl; };
-struct dsm_lm { LmImpl* impl; };
-struct dsm_asr { AsrImpl* impl; dsm_mimi* mimi; dsm_lm* lm; };
 
 template <typename F>
 static dsm_status guarded(F&& f) {

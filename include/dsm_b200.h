@@ -37,7 +37,8 @@ enum {
   DSM_ERR_CUDA = -3,
   DSM_ERR_OOM = -4,
   DSM_ERR_UNSUPPORTED = -5,
-  DSM_ERR_MISSING_WEIGHT = -6
+  DSM_ERR_MISSING_WEIGHT = -6,
+  DSM_ERR_CAPACITY = -7 /* no free slot (the reference closes the socket with code 4000, protocol.rs:33) */
 };
 
 enum { DSM_F32 = 0, DSM_BF16 = 1, DSM_F16 = 2, DSM_U32 = 3 };
@@ -230,6 +231,49 @@ dsm_status dsm_asr_last_logits(dsm_asr* h, float* logits);
 /* Device-side timing of the last step (ms) measured with CUDA events on the handle's streams:
  * out[0] = whole step, out[1] = Mimi encode branch, out[2] = LM branch. */
 dsm_status dsm_asr_last_step_ms(dsm_asr* h, float out[3]);
+
+/* ---- batched step scheduler ---------------------------------------------------------------- */
+/* Host side of moshi-server's BatchedAsr (moshi-server/src/batched_asr.rs:216-717) without the network
+ * front end: a fixed pool of B slots with a PCM queue each; one tick gathers at most one frame per
+ * active slot into a pinned [B,1920] buffer, builds the mask, applies pending per-slot resets, runs
+ * dsm_asr_step_pcm and fans the results out per slot.  push_* may be called from other threads while a
+ * tick runs. */
+typedef struct dsm_sched dsm_sched;
+enum { DSM_SCHED_STEP = 0, DSM_SCHED_WORD = 1, DSM_SCHED_END_WORD = 2, DSM_SCHED_MARKER = 3, DSM_SCHED_READY = 4 };
+/* OutMsg (moshi-server/src/asr.rs:24-34) before detokenisation. */
+typedef struct dsm_sched_out {
+  int32_t kind;
+  int32_t slot;
+  uint64_t channel_id;    /* connection the message belongs to (a slot is re-used across connections) */
+  int32_t step_idx;
+  int32_t n_tokens;       /* WORD */
+  const uint32_t* tokens; /* WORD: valid until the next tick */
+  double time;            /* WORD start_time / END_WORD stop_time */
+  int32_t n_prs;          /* STEP */
+  const float* prs;       /* STEP: this slot's VAD head probabilities */
+  int64_t marker_id;      /* MARKER */
+  int64_t buffered_pcm;   /* STEP / READY: samples still queued for the slot */
+} dsm_sched_out;
+/* asr may be NULL for a dry scheduler (slot / queue / marker logic only, no device step); then
+ * batch_size_if_no_asr gives B. */
+dsm_status dsm_sched_create(dsm_asr* asr, int32_t batch_size_if_no_asr, dsm_sched** out);
+void dsm_sched_destroy(dsm_sched* h);
+/* BatchedAsr::channels (batched_asr.rs:795-808): takes a free slot or fails with DSM_ERR_CAPACITY.  The
+ * slot's model state is reset before its first step (InMsg::Init, :567-573). */
+dsm_status dsm_sched_open(dsm_sched* h, int32_t* slot, uint64_t* channel_id);
+dsm_status dsm_sched_close(dsm_sched* h, int32_t slot);                                   /* :633-652 */
+dsm_status dsm_sched_push_audio(dsm_sched* h, int32_t slot, const float* pcm, int64_t n); /* InMsg::Audio */
+dsm_status dsm_sched_push_marker(dsm_sched* h, int32_t slot, int64_t id);                 /* InMsg::Marker */
+/* One pass of encoder_loop + model_loop + post_process (:314-522, 655-717).  *stepped = 0 when no slot had
+ * a full frame (the reference then sleeps 2 ms, :398-400). */
+dsm_status dsm_sched_tick(dsm_sched* h, int32_t* stepped);
+int32_t dsm_sched_out_count(const dsm_sched* h);
+dsm_status dsm_sched_out_get(const dsm_sched* h, int32_t i, dsm_sched_out* out);
+int32_t dsm_sched_free_slots(const dsm_sched* h);
+int64_t dsm_sched_step_idx(const dsm_sched* h);
+/* The mask [B] and the gathered batch [B,1920] of the last tick (host memory; for tests). */
+const uint8_t* dsm_sched_last_mask(const dsm_sched* h);
+const float* dsm_sched_batch_pcm(const dsm_sched* h);
 
 #ifdef __cplusplus
 }

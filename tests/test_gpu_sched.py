@@ -1,0 +1,60 @@
+"""The scheduler drives the same ASR state as manual step_pcm calls: streams that join late, pause and
+leave produce, per connection, exactly the tokens/messages of an AsrState fed the same frames and mask."""
+import numpy as np
+import pytest
+
+from helpers import frame, lm_weights, mimi_weights, synth_audio, tiny_lm, tiny_mimi
+
+pytestmark = pytest.mark.gpu
+
+
+def test_scheduler_matches_manual_stepping():
+    from dsm_b200 import api
+    B, frames = 3, 10
+    mspec, lspec = tiny_mimi(), tiny_lm(text_in_vocab_size=9, text_out_vocab_size=8)
+    mw, lw = mimi_weights(mspec, seed=0, layer_scale=0.5, decoder=False), lm_weights(lspec, seed=0)
+
+    def build():
+        m = api.Mimi(mspec, mw, B, decoder=False)
+        l = api.LmModel(lspec, lw, B)
+        return api.AsrState(m, l), m, l
+
+    asr_s, *keep_s = build()
+    sched = api.BatchedAsr(asr_s)
+    asr_m, *keep_m = build()
+    audio = synth_audio(B, frames)
+
+    # slot 0 streams from tick 0, slot 1 joins at tick 2, slot 0 pauses at ticks 4-5
+    s0, _ = sched.open()
+    s1 = None
+    cursor = {0: 0, 1: 0}
+    for tick in range(frames):
+        if tick == 2:
+            s1, _ = sched.open()
+        feed = {s0: not (4 <= tick <= 5)}
+        if s1 is not None:
+            feed[s1] = True
+        mask = np.zeros(B, np.uint8)
+        pcm = np.zeros((B, 1920), np.float32)
+        for slot, on in feed.items():
+            if on:
+                fr = frame(audio, cursor[slot])[slot]
+                sched.push_audio(slot, fr[:700])              # arbitrary packetisation
+                sched.push_audio(slot, fr[700:])
+                pcm[slot], mask[slot] = fr, 1
+                cursor[slot] += 1
+        if tick == 2:
+            asr_m.reset_batch_idx(s1)                         # what InMsg::Init does for a new connection
+        if tick == 0:
+            asr_m.reset_batch_idx(s0)
+        stepped, outs = sched.tick()
+        assert stepped == bool(mask.any())
+        assert sched.last_mask().tolist() == mask.tolist()
+        manual = asr_m.step_pcm(pcm, mask)
+        assert (asr_s.last_tokens[mask.astype(bool)] == asr_m.last_tokens[mask.astype(bool)]).all()
+        words_s = sorted((o["slot"], tuple(o["tokens"]), o["start_time"]) for o in outs if o["kind"] == "word")
+        words_m = sorted((m[3], tuple(m[1]), m[2]) for m in manual if m[0] == "word")
+        assert words_s == words_m
+        steps = [o for o in outs if o["kind"] == "step"]
+        assert sorted(o["slot"] for o in steps) == [i for i in range(B) if mask[i]]
+        assert all(len(o["prs"]) == lspec.extra_heads_num for o in steps)
