@@ -51,7 +51,10 @@ def test_scheduler_matches_manual_stepping():
         assert stepped == bool(mask.any())
         assert sched.last_mask().tolist() == mask.tolist()
         manual = asr_m.step_pcm(pcm, mask)
-        assert (asr_s.last_tokens[mask.astype(bool)] == asr_m.last_tokens[mask.astype(bool)]).all()
+        act = mask.astype(bool)
+        if act.any():
+            # the scheduler steps the C++ state directly; read its sampled tokens back through the logits
+            assert (asr_s.last_logits().argmax(-1)[act] == asr_m.last_tokens[act]).all()
         words_s = sorted((o["slot"], tuple(o["tokens"]), o["start_time"]) for o in outs if o["kind"] == "word")
         words_m = sorted((m[3], tuple(m[1]), m[2]) for m in manual if m[0] == "word")
         assert words_s == words_m
