@@ -124,10 +124,12 @@ struct TcParams {
   int atomic;        // ACCUM with split-K: combine with red.global.add.f32
 };
 
-template <int BMX, int MODE, int STAGES>
+// NACC weight sub-tiles (accumulators) per CTA: the gate/value pair, or two consecutive 128-row tiles
+// ("wide" CTAs halve how often the activation slab is pulled through L2 per weight byte).
+template <int BMX, int MODE, int NACC, int STAGES>
 __global__ void __launch_bounds__(128, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
-  constexpr int NACC = MODE == TC_GATE_BF16 ? 2 : 1;
+  static_assert(MODE != TC_GATE_BF16 || NACC == 2, "the gated epilogue needs the gate and value accumulators");
   constexpr int A_BYTES = TC_BN * TC_BK * 2;          // 16 KB
   constexpr int B_BYTES = BMX * TC_BK * 2;
   constexpr int STAGE_BYTES = NACC * A_BYTES + B_BYTES;
@@ -143,7 +145,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int n0 = blockIdx.x * TC_BN;       // weight-row tile (GATE: gate row j0 = n0, value row hidden + n0)
+  // weight-row tile: GATE -> gate rows [n0, n0+128) and value rows hidden + the same; otherwise NACC
+  // consecutive 128-row tiles starting at n0
+  const int n0 = blockIdx.x * TC_BN * (MODE == TC_GATE_BF16 ? 1 : NACC);
+  const int second = MODE == TC_GATE_BF16 ? p.hidden + n0 : n0 + TC_BN;
   const int m0 = blockIdx.y * BMX;         // stream tile
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int num_kb = min(p.kb_per_split, p.kb_total - kb_begin);
@@ -177,7 +182,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       uint8_t* st = smem + s * STAGE_BYTES;
       const int kc = k0 + kb * TC_BK;
       tma_load_2d(st, &map_w, kc, n0, &full_bar[s]);
-      if (NACC == 2) tma_load_2d(st + A_BYTES, &map_w, kc, p.hidden + n0, &full_bar[s]);
+      if (NACC == 2) tma_load_2d(st + A_BYTES, &map_w, kc, second, &full_bar[s]);
       tma_load_2d(st + NACC * A_BYTES, &map_x, kc, m0, &full_bar[s]);
     }
   } else if (warp == 1 && lane == 0) {
@@ -210,33 +215,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   __syncwarp();
   mbar_wait(accum_bar, 0);
   tc_fence_after();
-  const int n = n0 + warp * 32 + lane;                       // this thread's weight row
   const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const int n_limit = MODE == TC_GATE_BF16 ? p.hidden : p.N;
+  if (MODE == TC_GATE_BF16) {
+    const int n = n0 + warp * 32 + lane;                     // this thread's gate row
 #pragma unroll 1
-  for (int c = 0; c < BMX; c += 32) {
-    if (m0 + c >= p.M) break;                                // warp-uniform: whole chunk out of range
-    float v[32];
-    tmem_ld32(lane_addr + c, v);
-    if (MODE == TC_GATE_BF16) {
-      float u[32];
+    for (int c = 0; c < BMX; c += 32) {
+      if (m0 + c >= p.M) break;                              // warp-uniform: whole chunk out of range
+      float v[32], u[32];
+      tmem_ld32(lane_addr + c, v);
       tmem_ld32(lane_addr + BMX + c, u);
-      if (n < n_limit) {
+      if (n < p.hidden) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int m = m0 + c + i;
           if (m < p.M) p.out_bf16[(long long)m * p.hidden + n] = __float2bfloat16_rn(silu(v[i]) * u[i]);
         }
       }
-    } else if (n < n_limit) {
+    }
+  } else {
+#pragma unroll 1
+    for (int a = 0; a < NACC; ++a) {
+      const int n = n0 + a * TC_BN + warp * 32 + lane;       // this thread's weight row in sub-tile a
+#pragma unroll 1
+      for (int c = 0; c < BMX; c += 32) {
+        if (m0 + c >= p.M) break;
+        float v[32];
+        tmem_ld32(lane_addr + a * BMX + c, v);
+        if (n < p.N) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int m = m0 + c + i;
-        if (m < p.M) {
-          float* dst = p.out_f32 + (long long)m * p.N + n;
-          if (p.atomic) atomicAdd(dst, v[i]);
-          else if (MODE == TC_STORE_F32) *dst = v[i];
-          else *dst += v[i];
+          for (int i = 0; i < 32; ++i) {
+            const int m = m0 + c + i;
+            if (m < p.M) {
+              float* dst = p.out_f32 + (long long)m * p.N + n;
+              if (p.atomic) atomicAdd(dst, v[i]);
+              else if (MODE == TC_STORE_F32) *dst = v[i];
+              else *dst += v[i];
+            }
+          }
         }
       }
     }
@@ -286,19 +301,18 @@ bool tc_gemm_supported(int M, int N, int K, int mode) {
   return true;
 }
 
-template <int BMX, int MODE>
+template <int BMX, int MODE, int NACC>
 struct TcCfg {
-  static constexpr int NACC = MODE == TC_GATE_BF16 ? 2 : 1;
   static constexpr int STAGE_BYTES = NACC * TC_BN * TC_BK * 2 + BMX * TC_BK * 2;
   static constexpr int RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = RAW > 8 ? 8 : RAW;
   static constexpr int SMEM = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
 };
 
-template <int BMX, int MODE>
+template <int BMX, int MODE, int NACC>
 static void launch_tc(const TcGemm& g, cudaStream_t st) {
-  using C = TcCfg<BMX, MODE>;
-  auto kern = tc_gemm_kernel<BMX, MODE, C::STAGES>;
+  using C = TcCfg<BMX, MODE, NACC>;
+  auto kern = tc_gemm_kernel<BMX, MODE, NACC, C::STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
     DSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -311,7 +325,7 @@ static void launch_tc(const TcGemm& g, cudaStream_t st) {
   DSM_CHECK(ceil_div(p.kb_total, p.kb_per_split) == g.split_k, DSM_ERR_INVALID_ARG, "tc_gemm: split_k %d leaves an empty split", g.split_k);
   p.out_f32 = g.out_f32, p.out_bf16 = g.out_bf16, p.atomic = g.split_k > 1;
   const int n_rows = MODE == TC_GATE_BF16 ? g.hidden : g.N;
-  dim3 grid(ceil_div(n_rows, TC_BN), ceil_div(g.M, BMX), g.split_k);
+  dim3 grid(ceil_div(n_rows, TC_BN * (MODE == TC_GATE_BF16 ? 1 : NACC)), ceil_div(g.M, BMX), g.split_k);
   if (MODE == TC_STORE_F32 && g.split_k > 1)   // partial sums are combined by atomics onto zeros
     DSM_CUDA(cudaMemsetAsync(g.out_f32, 0, (size_t)g.M * g.N * sizeof(float), st));
   kern<<<grid, 128, C::SMEM, st>>>(g.map_w, g.map_x, p);
@@ -325,14 +339,17 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
   g.M = M, g.N = N, g.K = K, g.mode = mode, g.out_f32 = out_f32, g.out_bf16 = out_bf16;
   g.hidden = mode == TC_GATE_BF16 ? N / 2 : 0;
   const int n_rows = mode == TC_GATE_BF16 ? g.hidden : N;
-  const int n_tiles = ceil_div(n_rows, TC_BN);
+  // Wide CTAs (two weight sub-tiles per CTA) halve the activation re-reads but also halve the CTA count
+  // and double the epilogue; measured slower at 256 streams (LM step 5.85 ms vs 5.15 ms), so they are
+  // opt-in (DSM_TC_WIDE=1) for experiments with larger batches.
+  static const bool wide = [] { const char* e = getenv("DSM_TC_WIDE"); return e && e[0] == '1'; }();
+  g.nacc = mode == TC_GATE_BF16 ? 2 : ((wide && n_rows >= 2 * TC_BN) ? 2 : 1);
+  const int n_tiles = ceil_div(n_rows, TC_BN * (mode == TC_GATE_BF16 ? 1 : g.nacc));
   // Stream tile: as wide as the batch allows.  Every CTA must pull its W slab AND its X slab through
   // the SM's L2 port, so narrower stream tiles multiply the X traffic; to cover the 148 SMs we split K
   // instead (same total bytes, more CTAs) and combine the partial sums with f32 atomics.  The gate
-  // pair needs two accumulators (2 x 128 columns) and a non-linear epilogue, so it neither widens
-  // past 128 nor splits.
-  const int max_bmx = mode == TC_GATE_BF16 ? 128 : 256;
-  g.bmx = M <= 64 ? 64 : (M <= 128 ? 128 : max_bmx);
+  // pair has a non-linear epilogue, so it does not split.
+  g.bmx = M <= 64 ? 64 : (M <= 128 ? 128 : ((mode == TC_GATE_BF16 && !wide) ? 128 : 256));
   g.split_k = 1;
   if (mode != TC_GATE_BF16) {
     const int kb = K / TC_BK;
@@ -352,26 +369,15 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
 }
 
 void tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
-#define TC_DISPATCH(MODE)                                  \
-  switch (g.bmx) {                                         \
-    case 64: return launch_tc<64, MODE>(g, st);            \
-    case 128: return launch_tc<128, MODE>(g, st);          \
-    case 256: return launch_tc<256, MODE>(g, st);          \
-    default: break;                                        \
-  }
-  if (g.mode == TC_STORE_F32) {
-    TC_DISPATCH(TC_STORE_F32)
-  } else if (g.mode == TC_ACCUM_F32) {
-    TC_DISPATCH(TC_ACCUM_F32)
-  } else {
-    switch (g.bmx) {
-      case 64: return launch_tc<64, TC_GATE_BF16>(g, st);
-      case 128: return launch_tc<128, TC_GATE_BF16>(g, st);
-      default: break;
-    }
-  }
-#undef TC_DISPATCH
-  fail(DSM_ERR_UNSUPPORTED, "tc_gemm: no kernel for bmx=%d mode=%d", g.bmx, g.mode);
+#define TC_CASE(BMX, MODE, NACC) \
+  if (g.bmx == BMX && g.mode == MODE && g.nacc == NACC) return launch_tc<BMX, MODE, NACC>(g, st);
+  TC_CASE(64, TC_STORE_F32, 1) TC_CASE(128, TC_STORE_F32, 1) TC_CASE(256, TC_STORE_F32, 1)
+  TC_CASE(64, TC_STORE_F32, 2) TC_CASE(128, TC_STORE_F32, 2) TC_CASE(256, TC_STORE_F32, 2)
+  TC_CASE(64, TC_ACCUM_F32, 1) TC_CASE(128, TC_ACCUM_F32, 1) TC_CASE(256, TC_ACCUM_F32, 1)
+  TC_CASE(64, TC_ACCUM_F32, 2) TC_CASE(128, TC_ACCUM_F32, 2) TC_CASE(256, TC_ACCUM_F32, 2)
+  TC_CASE(64, TC_GATE_BF16, 2) TC_CASE(128, TC_GATE_BF16, 2) TC_CASE(256, TC_GATE_BF16, 2)
+#undef TC_CASE
+  fail(DSM_ERR_UNSUPPORTED, "tc_gemm: no kernel for bmx=%d mode=%d nacc=%d", g.bmx, g.mode, g.nacc);
 }
 
 }  // namespace dsm

@@ -27,6 +27,7 @@ struct TcGemm {
   CUtensorMap map_x;   // [M, K] bf16, box 64 x BMX
   int M = 0, N = 0, K = 0;
   int bmx = 0;         // streams per tile: 64, 128 or 256
+  int nacc = 1;        // weight sub-tiles (TMEM accumulators) per CTA
   int split_k = 1;
   int mode = TC_STORE_F32;
   int hidden = 0;      // TC_GATE_BF16: N = 2 * hidden

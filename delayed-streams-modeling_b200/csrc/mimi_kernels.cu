@@ -335,28 +335,35 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
     return pj;
   };
 
-  for (int j0 = warp * 2; j0 < context; j0 += 8) {
-    const int j = j0 + sub;
-    float part[TQ];
+  // 4 warps x 2 keys x UNR keys in flight per iteration: the loads are issued together (memory-level
+  // parallelism), then reduced
+  constexpr int UNR = 4;
+  for (int j0 = warp * 2 * UNR; j0 < context; j0 += 8 * UNR) {
+    float4 kv[UNR];
 #pragma unroll
-    for (int s = 0; s < TQ; ++s) part[s] = 0.f;
-    if (j < context) {
-      float4 kv = *reinterpret_cast<const float4*>(kb + (long long)j * D + c4 * 4);
-#pragma unroll
-      for (int s = 0; s < TQ; ++s) part[s] = q[s].x * kv.x + q[s].y * kv.y + q[s].z * kv.z + q[s].w * kv.w;
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + 2 * u + sub;
+      kv[u] = j < context ? __ldg(reinterpret_cast<const float4*>(kb + (long long)j * D + c4 * 4))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int s = 0; s < TQ; ++s) {
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) part[s] += __shfl_xor_sync(0xffffffffu, part[s], o);
-    }
-    if (c4 == 0 && j < context) {
-      const long long pj = active ? slot_pos(j) : 0;
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + 2 * u + sub;
+      float part[TQ];
 #pragma unroll
       for (int s = 0; s < TQ; ++s) {
-        if (s < t) {
-          const bool vis = !active || pj <= p0 + s;
-          sc[s * context + j] = vis ? part[s] * scale : -INFINITY;
+        part[s] = q[s].x * kv[u].x + q[s].y * kv[u].y + q[s].z * kv[u].z + q[s].w * kv[u].w;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) part[s] += __shfl_xor_sync(0xffffffffu, part[s], o);
+      }
+      if (c4 == 0 && j < context) {
+        const long long pj = active ? slot_pos(j) : 0;
+#pragma unroll
+        for (int s = 0; s < TQ; ++s) {
+          if (s < t) {
+            const bool vis = !active || pj <= p0 + s;
+            sc[s * context + j] = vis ? part[s] * scale : -INFINITY;
+          }
         }
       }
     }
@@ -386,15 +393,26 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
   float4 acc[TQ];
 #pragma unroll
   for (int s = 0; s < TQ; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j = g; j < context; j += 8) {
-    float4 v = *reinterpret_cast<const float4*>(vb + (long long)j * D + d4 * 4);
+  for (int j0 = g; j0 < context; j0 += 8 * UNR) {
+    float4 vv[UNR];
 #pragma unroll
-    for (int s = 0; s < TQ; ++s) {
-      const float p = sc[s * context + j];
-      acc[s].x = fmaf(p, v.x, acc[s].x);
-      acc[s].y = fmaf(p, v.y, acc[s].y);
-      acc[s].z = fmaf(p, v.z, acc[s].z);
-      acc[s].w = fmaf(p, v.w, acc[s].w);
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + 8 * u;
+      vv[u] = j < context ? __ldg(reinterpret_cast<const float4*>(vb + (long long)j * D + d4 * 4))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + 8 * u;
+      if (j >= context) break;
+#pragma unroll
+      for (int s = 0; s < TQ; ++s) {
+        const float p = sc[s * context + j];
+        acc[s].x = fmaf(p, vv[u].x, acc[s].x);
+        acc[s].y = fmaf(p, vv[u].y, acc[s].y);
+        acc[s].z = fmaf(p, vv[u].z, acc[s].z);
+        acc[s].w = fmaf(p, vv[u].w, acc[s].w);
+      }
     }
   }
 #pragma unroll
