@@ -350,12 +350,16 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
   // instead (same total bytes, more CTAs) and combine the partial sums with f32 atomics.  The gate
   // pair has a non-linear epilogue, so it does not split.
   g.bmx = M <= 64 ? 64 : (M <= 128 ? 128 : ((mode == TC_GATE_BF16 && !wide) ? 128 : 256));
+  // experiment knobs: DSM_TC_BMX forces the stream tile, DSM_TC_MAXSPLIT caps split-K
+  static const int env_bmx = [] { const char* e = getenv("DSM_TC_BMX"); return e ? atoi(e) : 0; }();
+  static const int env_split = [] { const char* e = getenv("DSM_TC_MAXSPLIT"); return e ? atoi(e) : 16; }();
+  if (env_bmx && mode != TC_GATE_BF16 && M > env_bmx / 2) g.bmx = env_bmx;
   g.split_k = 1;
   if (mode != TC_GATE_BF16) {
     const int kb = K / TC_BK;
     const long long base = (long long)n_tiles * ceil_div(M, g.bmx);
     double best = 0.0;
-    for (int s = 1; s <= 16; ++s) {
+    for (int s = 1; s <= env_split; ++s) {
       const int per = ceil_div(kb, s);
       if (per < 4 && s > 1) break;
       const int s_eff = ceil_div(kb, per);

@@ -138,6 +138,16 @@ void launch_rope_scatter_bf16(const float* qkv, const RingState& rs, int B, int 
 // warp-wide load instruction fetches 32*16 B = 512 contiguous bytes (256/D keys... 2 keys at D=128,
 // 4 at D=64); loads are unrolled UNROLL deep to keep >= 4 KB per warp in flight.
 // ================================================================================================
+// 16-byte streaming load that does not allocate in L1 (the rings are read exactly once per step), so the
+// kernel's bandwidth does not depend on how much of the SM's L1/shared array is carved out as L1.
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
 template <int D, int UNROLL>
 __global__ void __launch_bounds__(128) lm_attention_kernel(const __nv_bfloat16* __restrict__ q, RingState rs,
                                                             const uint8_t* __restrict__ mask, int H, int context,
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(128) lm_attention_kernel(const __nv_bfloat16* 
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const int j = j0 + u * KPW + sub;
-      kv[u] = j < n ? __ldg(reinterpret_cast<const uint4*>(kb + (long long)j * D + c8 * 8)) : make_uint4(0, 0, 0, 0);
+      kv[u] = j < n ? ld_stream16(kb + (long long)j * D + c8 * 8) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -231,7 +241,7 @@ __global__ void __launch_bounds__(128) lm_attention_kernel(const __nv_bfloat16* 
     for (int u = 0; u < UNROLL; ++u) {
       const int j = j0 + u * KPW + sub;
       const bool ok = j < n;
-      vv[u] = ok ? __ldg(reinterpret_cast<const uint4*>(vb + (long long)j * D + c8 * 8)) : make_uint4(0, 0, 0, 0);
+      vv[u] = ok ? ld_stream16(vb + (long long)j * D + c8 * 8) : make_uint4(0, 0, 0, 0);
       pj[u] = ok ? sc[j] : 0.f;
     }
 #pragma unroll
@@ -268,6 +278,19 @@ void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint
                          int context, const __nv_bfloat16* k_ring, const __nv_bfloat16* v_ring, __nv_bfloat16* out,
                          cudaStream_t st) {
   size_t smem = (size_t)std::max(context, 4 * D) * sizeof(float);
+  // DSM_ATTN_CARVEOUT=1: request the maximum shared-memory carve-out so attention CTAs can share an SM
+  // with the codec's tensor-core GEMMs (an SM only hosts kernels that agree on the carve-out)
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    const char* e = getenv("DSM_ATTN_CARVEOUT");
+    if (e && e[0] == '1') {
+      DSM_CUDA(cudaFuncSetAttribute(lm_attention_kernel<128, 8>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
+      DSM_CUDA(cudaFuncSetAttribute(lm_attention_kernel<64, 8>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
+    }
+    carveout_set = true;
+  }
   if (D == 128)
     lm_attention_kernel<128, 8><<<B * H, 128, smem, st>>>(q, rs, mask, H, context, k_ring, v_ring, out);
   else if (D == 64)
