@@ -18,10 +18,14 @@ Parity pinning status (see DESIGN.md "Oracle"):
     (``kv_cache.rs:338-405`` -> ``tests/test_oracle_kv_cache.py``) and streaming == one-shot for
     conv1d / conv-transpose1d over the reference's grid (``conv.rs:698-723`` ->
     ``tests/test_oracle_conv.py``).
-  * Cross-checked against the independent HF ``transformers`` Mimi implementation with shared random
-    weights (``tests/test_oracle_hf_mimi.py``) where that package is importable.
-  * PARITY UNPINNED for everything the reference has no tests or golden vectors for: Mimi code
-    indices, RVQ, LM logits, ASR transcripts.  For those the oracle is a line-by-line restatement,
-    each function citing the file:line it follows; un-vendored candle op semantics it assumes are
-    listed in SURVEY.md Appendix C.
+  * CROSS-CHECKED against independent implementations of the same models, the HF ``transformers``
+    ``MimiModel`` and ``KyutaiSpeechToTextModel``, loaded with the SAME random weights:
+    encoder latents + RVQ codes and decoded audio (``tests/test_oracle_hf_mimi.py``), LM hidden
+    states + greedy tokens (``tests/test_oracle_hf_lm.py``).  This pins the architecture (layer
+    order, strides, paddings, ELU / LayerScale / gating placement, RoPE pairing, RVQ residual
+    updates); it does not pin candle's rounding.
+  * PARITY UNPINNED against the reference's own outputs: the reference has no tests, golden
+    vectors or fixtures for Mimi codes, RVQ indices, LM logits or transcripts, and it cannot be
+    built here to generate any.  Un-vendored candle op semantics the oracle assumes are listed in
+    SURVEY.md Appendix C.
 """
