@@ -1,0 +1,49 @@
+"""BASELINE config 1 as a parity case: the stt-1b-en_fr architecture at batch 1, streaming the reference's
+bundled speech sample frame by frame (zero-padded tail, then asr_delay + 2 flush frames as SURVEY.md
+Appendix A describes), GPU path vs CPU oracle: RVQ codes identical, logits within rel 1e-2, greedy tokens
+identical.  Weights are seeded random init (no checkpoint offline), so the "transcript" is token ids."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, LmSpec, MimiSpec, lm_weights, mimi_weights, oracle_lm_weights, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_stt_1b_batch1_on_bundled_speech():
+    from dsm_b200 import api
+    from oracle.lm import AsrState as OAsr, LmModel as OLm
+    from oracle.mimi import Mimi as OMimi
+    torch.set_num_threads(os.cpu_count() or 8)
+    pcm = np.load(f"{GOLDEN}/speech_24k_int16.npy").astype(np.float32) / 32768.0
+    mspec, lspec = MimiSpec(), LmSpec()                       # Mimi v0_1 (n_q 32) + stt-1b-en_fr
+    n_audio = 24                                              # first ~1.9 s of speech keeps the CPU oracle quick
+    frames = n_audio + lspec.asr_delay_in_tokens + 2
+    audio = np.zeros(frames * 1920, np.float32)
+    audio[:n_audio * 1920] = pcm[:n_audio * 1920]
+    mw = mimi_weights(mspec, seed=0, layer_scale=0.5, decoder=False)
+    lw = lm_weights(lspec, seed=0)
+    g_mimi, g_lm = api.Mimi(mspec, mw, 1, decoder=False), api.LmModel(lspec, lw, 1)
+    g = api.AsrState(g_mimi, g_lm)
+    probe = api.Mimi(mspec, mw, 1, decoder=False)
+    o_mimi = OMimi(mspec, mw, 1, decoder=False)
+    o = OAsr(1, lspec.asr_delay_in_tokens, o_mimi, OLm(lspec, oracle_lm_weights(lw), 1))
+    o_probe = OMimi(mspec, mw, 1, decoder=False)
+    same_codes = same_tok = 0
+    worst = 0.0
+    for i in range(frames):
+        fr = audio[i * 1920:(i + 1) * 1920].reshape(1, 1920)
+        gc = probe.encode_step(fr)
+        oc = o_probe.encode_step(torch.from_numpy(fr).unsqueeze(1))[:, :, 0].numpy()
+        same_codes += int((gc.astype(np.int64) == oc).all())
+        gm = g.step_pcm(fr)
+        om = o.step_pcm(torch.from_numpy(fr).unsqueeze(1))
+        worst = max(worst, rel_err(g.last_logits(), o.last_logits.numpy()))
+        same_tok += int(g.last_tokens[0] == o.last_tokens.numpy()[0])
+        assert [m[0] for m in gm] == [m[0] for m in om]
+    assert same_codes >= 0.995 * frames, f"RVQ codes identical on {same_codes}/{frames} frames"
+    assert worst < 1e-2, f"logits rel err {worst:.3e}"
+    assert same_tok == frames, f"greedy tokens identical on {same_tok}/{frames} frames"
