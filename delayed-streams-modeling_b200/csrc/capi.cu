@@ -162,7 +162,7 @@ dsm_status dsm_debug_gemm_f32(int32_t impl, int32_t B, int32_t T, int64_t stride
     if (impl == 1) {
       DSM_CHECK(tc6_supported(g), DSM_ERR_UNSUPPORTED, "shape not supported by the tensor-core codec GEMM");
       Tc6Gemm t;
-      tc6_prepare(t, g, tc6_split_weights(a, hw, N, K));
+      tc6_prepare(t, g, tc6_split_weights(a, hw, N, K), tc6_make_workspace(a));
       tc6_launch(t, 0);
     } else {
       g.W = a.upload(hw);

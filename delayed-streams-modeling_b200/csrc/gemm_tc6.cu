@@ -149,6 +149,9 @@ struct Tc6Params {
   int n_groups;        // ceil(N / (nj * BN))
   int nj;              // column sub-tiles per tile
   int pm;              // main-term accumulators the k-blocks rotate over (see the MMA issuer)
+  int split_k;         // K splits per tile (work item = (tile, split)); partials meet in `ws`
+  float* ws;           // [tiles * split_k][128][nj * BN] partial sums (split_k > 1)
+  int* counters;       // [tiles] arrivals; the last split to arrive reduces in split order and stores
   const float* bias;
   int neg;
   const float* scale;
@@ -184,14 +187,17 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t* w_full = bars + 12;          // [WS]
   uint64_t* w_empty = w_full + WS;       // [WS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + WS);
+  uint32_t* last_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int num_kb = (p.K + T6_BK - 1) / T6_BK;
   const int rows_box = p.t_sub * p.b_sub;
-  const int pm = min(p.pm, num_kb);          // main accumulators actually written
   const int acc_stride = p.nj * BN;          // columns of one accumulator set
   const int buf_stride = (1 + p.pm) * acc_stride;   // columns of one tile's accumulators (<= 256)
   const int total_tiles = p.m_tiles * p.n_groups;
+  const int S = p.split_k;
+  const int kb_per = (num_kb + S - 1) / S;       // the host picks S so that no split is empty
+  const int total_items = total_tiles * S;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -221,10 +227,11 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     // ---------------- A producer: f32 conv-window tile -> staging ----------------
     int kit = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int tile = item / S, kb0 = (item % S) * kb_per, kbn = min(kb_per, num_kb - kb0);
       const int mt = tile / p.n_groups;
       const int t0 = (mt % p.t_tiles) * p.t_sub, b0 = (mt / p.t_tiles) * p.b_sub;
-      for (int kb = 0; kb < num_kb; ++kb, ++kit) {
+      for (int kb = kb0; kb < kb0 + kbn; ++kb, ++kit) {
         const int s = kit & 1;
         mbar_wait(&stg_empty[s], ((kit >> 1) & 1) ^ 1);
         const int kc = kb * T6_BK;
@@ -237,10 +244,11 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   } else if (warp == 3 && lane == 0) {
     // ---------------- W producer: three bf16 planes per (k-block, column sub-tile) ----------------
     int wit = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int tile = item / S, kb0 = (item % S) * kb_per, kbn = min(kb_per, num_kb - kb0);
       const int n0 = (tile % p.n_groups) * p.nj * BN;
       const int nj = min(p.nj, (p.N - n0 + BN - 1) / BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb0; kb < kb0 + kbn; ++kb) {
         for (int j = 0; j < nj; ++j, ++wit) {
           const int s = wit % WS;
           mbar_wait(&w_empty[s], ((wit / WS) & 1) ^ 1);
@@ -260,14 +268,16 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int pa[6] = {0, 1, 2, 0, 1, 0};
     const int pw[6] = {2, 1, 0, 1, 0, 0};
     int kit = 0, wit = 0, li = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+      const int tile = item / S, kbn = min(kb_per, num_kb - (item % S) * kb_per);
+      const int pm = min(p.pm, kbn);                       // main accumulators actually written
       const int n0 = (tile % p.n_groups) * p.nj * BN;
       const int nj = min(p.nj, (p.N - n0 + BN - 1) / BN);
       const int buf = li & 1;
       mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1);     // epilogue has drained this TMEM buffer
       tc_fence_after();
       const uint32_t acc_base = tmem_base + buf * buf_stride;
-      for (int kb = 0; kb < num_kb; ++kb, ++kit) {
+      for (int kb = 0; kb < kbn; ++kb, ++kit) {
         const int s = kit & 1;
         mbar_wait(&pl_full[s], (kit >> 1) & 1);
         tc_fence_after();
@@ -299,8 +309,9 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int r = (warp - 4) * 32 + lane;    // tile row
     const int sw = r & 7;
     int kit = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < num_kb; ++kb, ++kit) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int kb0 = (item % S) * kb_per, kbn = min(kb_per, num_kb - kb0);
+      for (int kb = kb0; kb < kb0 + kbn; ++kb, ++kit) {
         const int s = kit & 1;
         const uint32_t ph = (kit >> 1) & 1;
         const bool have2 = p.K - kb * T6_BK > 32;      // second 32-wide half present
@@ -358,7 +369,11 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     float* scratch = scratch_all + ew * (32 * 9);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     int li = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+      const int tile = item / S, split = item % S;
+      const int pm = min(p.pm, min(kb_per, num_kb - split * kb_per));
+      const int tile_n = p.nj * BN;
+      float* ws_mine = p.ws + ((size_t)(tile * S + split) * T6_BM + quad * 32) * tile_n;
       const int mt = tile / p.n_groups;
       const int t0 = (mt % p.t_tiles) * p.t_sub, b0 = (mt / p.t_tiles) * p.b_sub;
       const int n0 = (tile % p.n_groups) * p.nj * BN;
@@ -399,6 +414,16 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 8; ++i) scratch[lane * 9 + i] = v[h * 8 + i];
           __syncwarp();
+          if (S > 1) {
+            // split-K: park the raw partial sums of this (tile, split) in the workspace, coalesced
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int rr = 4 * q + qrow;
+              if (rr >= rr0 && rr < rr1) ws_mine[(size_t)rr * tile_n + c * 32 + h * 8 + cs] = scratch[rr * 9 + cs];
+            }
+            __syncwarp();
+            continue;
+          }
           const int col = n0 + c * 32 + h * 8 + cs;
           const bool col_ok = col < p.N;
           const float bias_l = (p.bias && col_ok) ? __ldg(p.bias + col) : 0.f;
@@ -431,6 +456,61 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (S > 1) {
+        // The split that arrives last for this tile adds all partials IN SPLIT ORDER (deterministic,
+        // unlike atomics) and runs the epilogue.
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(T6_EPI_WARPS * 32) : "memory");
+        if (ew == 0 && lane == 0) {
+          const int old = atomicAdd(p.counters + tile, 1);
+          const uint32_t last = old == S - 1 ? 1u : 0u;
+          if (last) p.counters[tile] = 0;      // ready for the next launch (graph replay)
+          *last_flag = last;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(T6_EPI_WARPS * 32) : "memory");
+        const bool is_last = *last_flag != 0;
+        if (is_last) {
+          // All eight epilogue warps sweep the tile linearly, four columns per thread, every split's
+          // partial in flight at once; each element is summed in split order.
+          __threadfence();
+          const float* ws_tile = p.ws + (size_t)tile * S * T6_BM * tile_n;
+          const size_t split_stride = (size_t)T6_BM * tile_n;
+          const int et = ew * 32 + lane;
+          const int tile_cols = min(tile_n, p.N - n0);
+          for (int e = et * 4; e < T6_BM * tile_n; e += T6_EPI_WARPS * 32 * 4) {
+            const int r = e / tile_n, cc = e - r * tile_n;
+            const int bl = r / p.t_sub, tl = r - bl * p.t_sub;
+            const int b = b0 + bl, t = t0 + tl;
+            if (r >= rows_box || b >= p.B || t >= p.T_out || cc >= tile_cols) continue;
+            const int m = b * p.T_out + t;
+            const int col = n0 + cc;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int sp = 0; sp < S; ++sp) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(ws_tile + sp * split_stride + e));
+              x.x += v.x, x.y += v.y, x.z += v.z, x.w += v.w;
+            }
+            float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float y = xs[i];
+              if (p.bias) y = p.neg ? __ldg(p.bias + col + i) - y : y + __ldg(p.bias + col + i);
+              if (p.act == 1) y = gelu_erf(y);
+              if (p.scale) y *= __ldg(p.scale + col + i);
+              xs[i] = y;
+            }
+            if (p.res) {
+              const float4 q = *reinterpret_cast<const float4*>(p.res + p.r_map.off(m) + col);
+              xs[0] += q.x, xs[1] += q.y, xs[2] += q.z, xs[3] += q.w;
+            }
+            if (p.out_raw)
+              *reinterpret_cast<float4*>(p.out_raw + p.o_map.off(m) + col) = make_float4(xs[0], xs[1], xs[2], xs[3]);
+            if (p.out_act)
+              *reinterpret_cast<float4*>(p.out_act + p.e_map.off(m) + col) =
+                  make_float4(elu_ref(xs[0]), elu_ref(xs[1]), elu_ref(xs[2]), elu_ref(xs[3]));
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(T6_EPI_WARPS * 32) : "memory");   // last_flag may be rewritten
+      }
     }
   }
   tc_fence_before();
@@ -465,7 +545,7 @@ struct T6Cfg {
   static constexpr int WS_RAW = (209 * 1024 - FIXED) / W_STAGE;
   static constexpr int WS = WS_RAW > 4 ? 4 : WS_RAW;
   static constexpr int SCRATCH = T6_EPI_WARPS * 32 * 9 * 4;
-  static constexpr int SMEM = FIXED + WS * W_STAGE + SCRATCH + (12 + 2 * WS) * 8 + 16;
+  static constexpr int SMEM = FIXED + WS * W_STAGE + SCRATCH + (12 + 2 * WS) * 8 + 16;   // barriers + tmem slot + last flag
   static_assert(SMEM <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static_assert(WS >= 2, "need at least two W stages");
 };
@@ -484,9 +564,10 @@ static void launch6(const Tc6Gemm& g, cudaStream_t st) {
   p.t_tiles = ceil_div(g.T_out, g.t_sub), p.nj = g.nj, p.pm = g.pm;
   p.m_tiles = p.t_tiles * ceil_div(g.B, g.b_sub);
   p.n_groups = ceil_div(g.N, g.nj * BN);
+  p.split_k = g.split_k, p.ws = g.ws, p.counters = g.counters;
   p.bias = g.ep.bias, p.neg = g.ep.neg, p.scale = g.ep.scale, p.res = g.ep.res, p.r_map = g.ep.r_map, p.act = g.ep.act;
   p.out_raw = g.ep.out_raw, p.o_map = g.ep.o_map, p.out_act = g.ep.out_act, p.e_map = g.ep.e_map;
-  const long long tiles = (long long)p.m_tiles * p.n_groups;
+  const long long tiles = (long long)p.m_tiles * p.n_groups * g.split_k;
   const int grid = (int)std::min<long long>(tiles, 148);
   kern<<<grid, T6_THREADS, C::SMEM, st>>>(g.map_a, g.map_w, p);
   check_launch("tc6_gemm");
@@ -531,7 +612,7 @@ __nv_bfloat16* tc6_split_weights(Arena& arena, const std::vector<float>& w, int 
   return d;
 }
 
-void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes) {
+void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes, const Tc6Workspace& wsp) {
   DSM_CHECK(tc6_supported(g), DSM_ERR_UNSUPPORTED, "tc6_gemm: unsupported problem M=%d N=%d K=%d", g.M, g.N, g.K);
   t.ep = g;
   t.K = g.K, t.N = g.N, t.T_out = g.a_map.T, t.B = g.M / g.a_map.T;
@@ -553,6 +634,25 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes)
   while (nj > 1 && m_tiles * ceil_div(n_sub, nj) < 148) nj = (nj + 1) / 2;
   t.nj = nj;
   t.pm = std::max(1, std::min(7, 256 / (nj * t.bn) - 1));
+  // Skinny problems (few tiles, long K) cannot fill 148 SMs with tiles alone: split K over several CTAs
+  // per tile; the partial sums meet in the shared workspace and the last arrival reduces them in order.
+  {
+    const long long tiles = m_tiles * ceil_div(n_sub, nj);
+    const int num_kb = ceil_div(g.K, T6_BK);
+    int S = 1;
+    // Measured at 256 streams: the fix-up pass and the extra per-CTA prologues cost what the shorter K loops
+    // save (codec step 3.94 ms with, 3.83 ms without), so deterministic split-K is opt-in
+    // (DSM_TC6_SPLITK=1) and only considered where >= 6 k-blocks remain per split.
+    static const bool splitk_on = [] { const char* e = getenv("DSM_TC6_SPLITK"); return e && e[0] == '1'; }();
+    if (splitk_on && wsp.ws && tiles <= 74 && num_kb >= 16) {
+      S = (int)std::max<long long>(1, std::min<long long>(148 / tiles, num_kb / 6));
+      const int per = ceil_div(num_kb, S);
+      S = ceil_div(num_kb, per);
+      const size_t need = (size_t)tiles * S * T6_BM * nj * t.bn * sizeof(float);
+      if (need > wsp.ws_bytes || tiles > wsp.n_counters) S = 1;
+    }
+    t.split_k = S, t.ws = wsp.ws, t.counters = wsp.counters;
+  }
   // A: f32 [B][T_out][K] window view, box 32 x t_sub x b_sub
   {
     cuuint64_t gdim[3] = {(cuuint64_t)g.K, (cuuint64_t)t.T_out, (cuuint64_t)t.B};
@@ -577,6 +677,15 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes)
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DSM_CHECK(r == CUDA_SUCCESS, DSM_ERR_CUDA, "tc6 W tensor map failed (%d): N=%d K=%d", (int)r, g.N, g.K);
   }
+}
+
+Tc6Workspace tc6_make_workspace(Arena& arena) {
+  Tc6Workspace w;
+  w.ws_bytes = (size_t)16 << 20;     // 148 work items x 128 rows x 128 columns x 4 B = 9.7 MB at most
+  w.ws = arena.alloc<float>(w.ws_bytes / sizeof(float));
+  w.n_counters = 1024;
+  w.counters = arena.alloc<int>(w.n_counters);
+  return w;
 }
 
 void tc6_launch(const Tc6Gemm& t, cudaStream_t st) {

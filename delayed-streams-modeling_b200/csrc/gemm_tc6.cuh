@@ -10,11 +10,23 @@
 
 namespace dsm {
 
+// Scratch shared by every split-K GEMM of one stream (they run one after another): partial-sum tiles and
+// per-tile arrival counters (zero between launches: the finishing CTA resets its counter).
+struct Tc6Workspace {
+  float* ws = nullptr;
+  size_t ws_bytes = 0;
+  int* counters = nullptr;
+  int n_counters = 0;
+};
+Tc6Workspace tc6_make_workspace(Arena& arena);
+
 struct Tc6Gemm {
   CUtensorMap map_a;   // f32 [B][T_out][K] window view of the activation buffer
   CUtensorMap map_w;   // bf16 [3][N][K] pre-split weight planes
   int K = 0, N = 0, T_out = 0, B = 0;
-  int t_sub = 0, b_sub = 0, bn = 0, nj = 0, pm = 1;
+  int t_sub = 0, b_sub = 0, bn = 0, nj = 0, pm = 1, split_k = 1;
+  float* ws = nullptr;
+  int* counters = nullptr;
   GemmParams ep;       // the problem as the CUDA-core GEMM would take it (epilogue fields are reused)
 };
 
@@ -22,7 +34,7 @@ struct Tc6Gemm {
 bool tc6_supported(const GemmParams& g);
 // Splits an f32 [N, K] weight matrix into three bf16 planes on the device ([3][N][K]).
 __nv_bfloat16* tc6_split_weights(Arena& arena, const std::vector<float>& w, int N, int K);
-void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes);
+void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes, const Tc6Workspace& wsp = Tc6Workspace());
 void tc6_launch(const Tc6Gemm& t, cudaStream_t st);
 
 }  // namespace dsm

@@ -36,14 +36,15 @@ bool codec_gemm_tc_enabled() {
   return !(e && std::string(e) == "simt");
 }
 
-std::shared_ptr<CodecGemm> make_codec_gemm(Arena& arena, const GemmParams& g, const std::vector<float>& w_host) {
+std::shared_ptr<CodecGemm> make_codec_gemm(Arena& arena, const GemmParams& g, const std::vector<float>& w_host,
+                                           const Tc6Workspace& wsp) {
   auto c = std::make_shared<CodecGemm>();
   c->g = g;
   DSM_CHECK(w_host.size() == (size_t)g.N * g.K, DSM_ERR_SHAPE, "codec gemm: weight has %zu elements, expected %d x %d",
             w_host.size(), g.N, g.K);
   c->use_tc = codec_gemm_tc_enabled() && tc6_supported(g);
   if (c->use_tc) {
-    tc6_prepare(c->t, g, tc6_split_weights(arena, w_host, g.N, g.K));
+    tc6_prepare(c->t, g, tc6_split_weights(arena, w_host, g.N, g.K), wsp);
   } else {
     c->g.W = arena.upload(w_host);
   }
@@ -107,19 +108,19 @@ void CodecTransformer::append_plan(Plan& plan, float* x, RowMap x_map, const uin
     GemmParams g;     // qkv = in_proj(norm1(x))
     g.A = xn, g.a_map = dense_rows(1, D), g.M = M, g.N = 3 * D, g.K = D;
     g.out_raw = qkv, g.o_map = dense_rows(1, 3 * D);
-    auto g_qkv = make_codec_gemm(*arena_, g, yl.h_in_proj);
+    auto g_qkv = make_codec_gemm(*arena_, g, yl.h_in_proj, wsp);
     GemmParams o;     // x <- x + layer_scale_1 * out_proj(attn)     (batched_transformer.rs:347-349)
     o.A = attn, o.a_map = dense_rows(1, D), o.M = M, o.N = D, o.K = D;
     o.scale = yl.ls1, o.res = x, o.r_map = x_map, o.out_raw = x, o.o_map = x_map;
-    auto g_out = make_codec_gemm(*arena_, o, yl.h_out_proj);
+    auto g_out = make_codec_gemm(*arena_, o, yl.h_out_proj, wsp);
     GemmParams f1;    // h = gelu(linear1(norm2(x)))
     f1.A = xn, f1.a_map = dense_rows(1, D), f1.M = M, f1.N = ff, f1.K = D;
     f1.act = 1, f1.out_raw = hbuf, f1.o_map = dense_rows(1, ff);
-    auto g_f1 = make_codec_gemm(*arena_, f1, yl.h_lin1);
+    auto g_f1 = make_codec_gemm(*arena_, f1, yl.h_lin1, wsp);
     GemmParams f2;    // x <- x + layer_scale_2 * linear2(h)   (:360-361)
     f2.A = hbuf, f2.a_map = dense_rows(1, ff), f2.M = M, f2.N = D, f2.K = ff;
     f2.scale = yl.ls2, f2.res = x, f2.r_map = x_map, f2.out_raw = x, f2.o_map = x_map;
-    auto g_f2 = make_codec_gemm(*arena_, f2, yl.h_lin2);
+    auto g_f2 = make_codec_gemm(*arena_, f2, yl.h_lin2, wsp);
     yl.h_in_proj = std::vector<float>();
     yl.h_out_proj = std::vector<float>();
     yl.h_lin1 = std::vector<float>();
@@ -350,7 +351,7 @@ static void build_seanet(const SeanetBuild& sb, const std::vector<SeanetLayer>& 
       g.res = res, g.r_map = res_map;
       g.out_raw = out_raw, g.o_map = raw_map;
       g.out_act = out_act, g.e_map = act_map;
-      auto cg = make_codec_gemm(arena, g, hW);
+      auto cg = make_codec_gemm(arena, g, hW, sb.m->wsp);
       sb.plan->push_back([=](cudaStream_t st) { run_codec_gemm(*cg, st); });
     }
   }
@@ -400,6 +401,7 @@ MimiImpl::MimiImpl(const dsm_mimi_spec& sp, const dsm_weights* w, int dev, int b
   d_first_step = arena.alloc<int>(1);
   d_first_step_dec = arena.alloc<int>(1);
   d_codes = arena.alloc<uint32_t>((size_t)B * spec.n_q);
+  if (codec_gemm_tc_enabled()) wsp = tc6_make_workspace(arena);
 
   // ---- codebooks (shared by encode and decode), quantization.rs:86-107 ----
   {
@@ -469,6 +471,7 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
   enc_plan.push_back([=](cudaStream_t st) {
     DSM_CUDA(cudaMemcpy2DAsync(dbg1, Tds * row_bytes, x, pitch, Tds * row_bytes, Bc, cudaMemcpyDeviceToDevice, st));
   });
+  enc_tr.wsp = wsp;
   enc_tr.init(arena, spec, B, "encoder_transformer", get);
   enc_tr.append_plan(enc_plan, x, x_map, d_mask);
   enc_plan.push_back([=](cudaStream_t st) {
@@ -482,7 +485,7 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
     g.A = x_ds, g.a_map = RowMap{1, (long long)(Sds + Tds) * D, (long long)ds * D};
     g.M = Bc, g.N = D, g.K = 2 * ds * D;
     g.out_raw = latent, g.o_map = dense_rows(1, D);
-    auto cg = make_codec_gemm(arena, g, conv_to_gemm(w, D, D, 2 * ds));
+    auto cg = make_codec_gemm(arena, g, conv_to_gemm(w, D, D, 2 * ds), wsp);
     enc_commits.push_back(CommitEntry{x_ds, x_ds + (long long)Tds * D, (long long)(Sds + Tds) * D, (long long)(Sds + Tds) * D, Sds * D, 1});
     float* xds = x_ds;
     int* first = d_first_step;
@@ -502,7 +505,7 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
     GemmParams gp;
     gp.A = latent, gp.a_map = dense_rows(1, D), gp.M = Bc, gp.N = 2 * qd, gp.K = D;
     gp.out_raw = resid, gp.o_map = dense_rows(1, 2 * qd);
-    auto g_proj = make_codec_gemm(arena, gp, wf);
+    auto g_proj = make_codec_gemm(arena, gp, wf, wsp);
     // codebook embeddings on the host once more for the score GEMMs' weight planes
     std::vector<float> emb_host((size_t)nq * bins * qd);
     DSM_CUDA(cudaMemcpy(emb_host.data(), emb_all, emb_host.size() * sizeof(float), cudaMemcpyDeviceToHost));
@@ -514,7 +517,7 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
       s.bias = c2_all + (size_t)q * bins, s.neg = 1;     // c2 - x.e   (quantization.rs:128-129)
       s.out_raw = scores, s.o_map = dense_rows(1, bins);
       std::vector<float> Eq(emb_host.begin() + (size_t)q * bins * qd, emb_host.begin() + (size_t)(q + 1) * bins * qd);
-      g_score[q] = make_codec_gemm(arena, s, Eq);
+      g_score[q] = make_codec_gemm(arena, s, Eq, wsp);
     }
     float* res = resid;
     float* sc = scores;
@@ -574,11 +577,11 @@ void MimiImpl::build_decoder(const GetFn& get, const WeightTable& wt) {
     GemmParams g1;
     g1.A = q_sum, g1.a_map = dense_rows(1, qd), g1.M = Bc, g1.N = D, g1.K = qd;
     g1.out_raw = dec_emb, g1.o_map = dense_rows(1, D);
-    auto cg1 = make_codec_gemm(arena, g1, wf);
+    auto cg1 = make_codec_gemm(arena, g1, wf, wsp);
     GemmParams g2;
     g2.A = q_sum + (size_t)Bc * qd, g2.a_map = dense_rows(1, qd), g2.M = Bc, g2.N = D, g2.K = qd;
     g2.res = dec_emb, g2.r_map = dense_rows(1, D), g2.out_raw = dec_emb, g2.o_map = dense_rows(1, D);
-    auto cg2 = make_codec_gemm(arena, g2, wr);
+    auto cg2 = make_codec_gemm(arena, g2, wr, wsp);
     dec_plan.push_back([=](cudaStream_t st) {
       launch_rvq_gather_sum(cin, nq, 0, 1, emb, bins, qd, Bc, qs, st);
       run_codec_gemm(*cg1, st);
@@ -590,6 +593,7 @@ void MimiImpl::build_decoder(const GetFn& get, const WeightTable& wt) {
     });
     dec_commits.push_back(CommitEntry{up_state, dec_emb, (long long)D, (long long)D, D, 0});
   }
+  dec_tr.wsp = wsp;
   dec_tr.init(arena, spec, B, "decoder_transformer", get);
   dec_tr.append_plan(dec_plan, x, x_map, d_mask);
 

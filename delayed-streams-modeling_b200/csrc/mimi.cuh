@@ -20,7 +20,8 @@ struct CodecGemm {
   bool use_tc = false;
 };
 bool codec_gemm_tc_enabled();
-std::shared_ptr<CodecGemm> make_codec_gemm(Arena& arena, const GemmParams& g, const std::vector<float>& w_host);
+std::shared_ptr<CodecGemm> make_codec_gemm(Arena& arena, const GemmParams& g, const std::vector<float>& w_host,
+                                           const Tc6Workspace& wsp = Tc6Workspace());
 void run_codec_gemm(const CodecGemm& c, cudaStream_t st);
 
 // One f32 streaming transformer with per-stream ring KV (batched_transformer.rs, Mimi flavour:
@@ -37,6 +38,7 @@ struct CodecTransformer {
     std::vector<float> h_in_proj, h_out_proj, h_lin1, h_lin2;   // host copies until the plan is built
   };
   Arena* arena_ = nullptr;
+  Tc6Workspace wsp;
   std::vector<Layer> layers;
   size_t kv_bytes = 0;
 
@@ -66,6 +68,7 @@ struct MimiImpl {
   uint32_t* h_codes = nullptr;     // pinned staging
   int* d_first_step = nullptr;     // 1 until the first encode step ran (left_pad_applied, conv.rs:232)
   int* d_first_step_dec = nullptr;
+  Tc6Workspace wsp;                // split-K scratch shared by the handle's codec GEMMs
 
   // ---- encoder ----
   float* d_pcm = nullptr;          // [B, 1920]
