@@ -137,6 +137,8 @@ constexpr int T6_PLANE = T6_BM * T6_BK * 2;      // 16 KB per bf16 plane tile
 constexpr int T6_EPI_WARPS = 8;      // two per TMEM lane quadrant
 constexpr int T6_CVT_WARPS = 4;      // one converter thread per tile row
 constexpr int T6_THREADS = (4 + T6_CVT_WARPS + T6_EPI_WARPS) * 32;
+constexpr int T6_SCR_LD = 36;        // floats per scratch row: 32 columns + 4 (float4 rows stay conflict-free)
+constexpr int T6_SCR = 16 * T6_SCR_LD;   // floats of one epilogue warp's transposition tile
 
 }  // namespace
 
@@ -176,8 +178,8 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint8_t* stg = smem;                           // [2][T6_STG]
   uint8_t* planes = stg + 2 * T6_STG;            // [2][3][T6_PLANE]
   uint8_t* wring = planes + 2 * 3 * T6_PLANE;    // [WS][W_STAGE]
-  float* scratch_all = reinterpret_cast<float*>(wring + WS * W_STAGE);   // [epilogue warps][32][9]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + T6_EPI_WARPS * 32 * 9);
+  float* scratch_all = reinterpret_cast<float*>(wring + WS * W_STAGE);   // [epilogue warps][16][36]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + T6_EPI_WARPS * T6_SCR);
   uint64_t* stg_full = bars;             // [2]
   uint64_t* stg_empty = bars + 2;        // [2]
   uint64_t* pl_full = bars + 4;          // [2]
@@ -366,7 +368,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // The two warps of a quadrant take alternate chunks; with a single chunk they split its rows.
     const int ew = warp - (4 + T6_CVT_WARPS);
     const int quad = warp & 3, sib = ew >> 2;     // sibling index 0/1 within the quadrant
-    float* scratch = scratch_all + ew * (32 * 9);
+    float* scratch = scratch_all + ew * T6_SCR;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     int li = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
@@ -393,8 +395,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const uint32_t acc_addr = lane_addr + buf * buf_stride;
       const int n_chunks = nj * BN / 32;
       const bool split_rows = n_chunks == 1;       // both siblings work on chunk 0, half the rows each
-      const int rr0 = split_rows ? sib * 16 : 0, rr1 = split_rows ? rr0 + 16 : 32;
-      const int qrow = lane >> 3, cs = lane & 7;   // 8 lanes per row: 32 contiguous bytes (one sector)
+      const int qrow = lane >> 3, cs = lane & 7;   // 8 lanes per row: 8 x float4 = one 128-byte segment
 #pragma unroll 1
       for (int c = split_rows ? 0 : sib; c < n_chunks; c += split_rows ? 1 : 2) {
         float v[32];
@@ -408,46 +409,63 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int i = 0; i < 16; ++i) v[h * 16 + i] += u[i];
           }
         }
+        // Transposition through shared memory, 16 rows x 32 columns at a time: the lanes that own the
+        // 16 TMEM rows park them as float4s in a [16][36] scratch tile, then all 32 lanes sweep it four
+        // rows per instruction (8 lanes x 16 B = one full 128-byte row segment), so every global access
+        // of the epilogue is a float4 in a fully used line.
+        const int col = n0 + c * 32 + cs * 4;
+        const bool col_ok = col < p.N;              // N is a multiple of 32: a chunk is valid as a whole
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), scale4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        if (p.scale && col_ok) scale4 = __ldg(reinterpret_cast<const float4*>(p.scale + col));
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          // 8 columns at a time through a [32][9] scratch tile
+        for (int half = 0; half < 2; ++half) {
+          if (split_rows && half != sib) continue;  // warp-uniform
+          if ((lane >> 4) == half) {
+            float4* dst = reinterpret_cast<float4*>(scratch + (lane & 15) * T6_SCR_LD);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) scratch[lane * 9 + i] = v[h * 8 + i];
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
           __syncwarp();
           if (S > 1) {
-            // split-K: park the raw partial sums of this (tile, split) in the workspace, coalesced
+            // split-K: park the raw partial sums of this (tile, split) in the workspace
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int rr = 4 * q + qrow;
-              if (rr >= rr0 && rr < rr1) ws_mine[(size_t)rr * tile_n + c * 32 + h * 8 + cs] = scratch[rr * 9 + cs];
+            for (int q = 0; q < 4; ++q) {
+              const int rr = half * 16 + 4 * q + qrow;
+              *reinterpret_cast<float4*>(ws_mine + (size_t)rr * tile_n + c * 32 + cs * 4) =
+                  *reinterpret_cast<const float4*>(scratch + (4 * q + qrow) * T6_SCR_LD + cs * 4);
             }
             __syncwarp();
             continue;
           }
-          const int col = n0 + c * 32 + h * 8 + cs;
-          const bool col_ok = col < p.N;
-          const float bias_l = (p.bias && col_ok) ? __ldg(p.bias + col) : 0.f;
-          const float scale_l = (p.scale && col_ok) ? __ldg(p.scale + col) : 1.f;
-          float rres[8];
-          const int nq = (rr1 - rr0) / 4;          // 4 or 8 row groups of 4 rows
+          float4 rres[4];
+          uint32_t wo[4], ao[4];
+          bool ok[4];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int rr = rr0 + 4 * q + qrow;
-            const uint32_t ro = __shfl_sync(0xffffffffu, res_off, rr & 31);
-            rres[q] = (q < nq && p.res && col_ok && ((ok_mask >> rr) & 1u)) ? __ldg(p.res + ro + col) : 0.f;
+          for (int q = 0; q < 4; ++q) {
+            const int rr = half * 16 + 4 * q + qrow;
+            const uint32_t ro = __shfl_sync(0xffffffffu, res_off, rr);
+            wo[q] = __shfl_sync(0xffffffffu, raw_off, rr);
+            ao[q] = __shfl_sync(0xffffffffu, act_off, rr);
+            ok[q] = col_ok && ((ok_mask >> rr) & 1u);
+            rres[q] = (p.res && ok[q]) ? __ldg(reinterpret_cast<const float4*>(p.res + ro + col))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int rr = rr0 + 4 * q + qrow;
-            const uint32_t wo = __shfl_sync(0xffffffffu, raw_off, rr & 31);
-            const uint32_t ao = __shfl_sync(0xffffffffu, act_off, rr & 31);
-            if (q >= nq || !col_ok || !((ok_mask >> rr) & 1u)) continue;
-            float x = scratch[rr * 9 + cs];
-            if (p.bias) x = p.neg ? bias_l - x : x + bias_l;
-            if (p.act == 1) x = gelu_erf(x);
-            x = x * scale_l + rres[q];
-            if (p.out_raw) p.out_raw[wo + col] = x;
-            if (p.out_act) p.out_act[ao + col] = elu_ref(x);
+          for (int q = 0; q < 4; ++q) {
+            if (!ok[q]) continue;
+            float4 x = *reinterpret_cast<const float4*>(scratch + (4 * q + qrow) * T6_SCR_LD + cs * 4);
+            if (p.bias) {
+              if (p.neg) x.x = bias4.x - x.x, x.y = bias4.y - x.y, x.z = bias4.z - x.z, x.w = bias4.w - x.w;
+              else x.x += bias4.x, x.y += bias4.y, x.z += bias4.z, x.w += bias4.w;
+            }
+            if (p.act == 1) x.x = gelu_erf(x.x), x.y = gelu_erf(x.y), x.z = gelu_erf(x.z), x.w = gelu_erf(x.w);
+            x.x = x.x * scale4.x + rres[q].x, x.y = x.y * scale4.y + rres[q].y;
+            x.z = x.z * scale4.z + rres[q].z, x.w = x.w * scale4.w + rres[q].w;
+            if (p.out_raw) *reinterpret_cast<float4*>(p.out_raw + wo[q] + col) = x;
+            if (p.out_act)
+              *reinterpret_cast<float4*>(p.out_act + ao[q] + col) =
+                  make_float4(elu_ref(x.x), elu_ref(x.y), elu_ref(x.z), elu_ref(x.w));
           }
           __syncwarp();
         }
@@ -544,7 +562,7 @@ struct T6Cfg {
   static constexpr int FIXED = 2 * T6_STG + 2 * 3 * T6_PLANE;             // 160 KB
   static constexpr int WS_RAW = (209 * 1024 - FIXED) / W_STAGE;
   static constexpr int WS = WS_RAW > 4 ? 4 : WS_RAW;
-  static constexpr int SCRATCH = T6_EPI_WARPS * 32 * 9 * 4;
+  static constexpr int SCRATCH = T6_EPI_WARPS * T6_SCR * 4;
   static constexpr int SMEM = FIXED + WS * W_STAGE + SCRATCH + (12 + 2 * WS) * 8 + 16;   // barriers + tmem slot + last flag
   static_assert(SMEM <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static_assert(WS >= 2, "need at least two W stages");
@@ -568,7 +586,8 @@ static void launch6(const Tc6Gemm& g, cudaStream_t st) {
   p.bias = g.ep.bias, p.neg = g.ep.neg, p.scale = g.ep.scale, p.res = g.ep.res, p.r_map = g.ep.r_map, p.act = g.ep.act;
   p.out_raw = g.ep.out_raw, p.o_map = g.ep.o_map, p.out_act = g.ep.out_act, p.e_map = g.ep.e_map;
   const long long tiles = (long long)p.m_tiles * p.n_groups * g.split_k;
-  const int grid = (int)std::min<long long>(tiles, 148);
+  static const int max_ctas = [] { const char* e = getenv("DSM_TC6_MAXCTAS"); int v = e ? atoi(e) : 0; return v > 0 ? v : 148; }();
+  const int grid = (int)std::min<long long>(tiles, max_ctas);
   kern<<<grid, T6_THREADS, C::SMEM, st>>>(g.map_a, g.map_w, p);
   check_launch("tc6_gemm");
 }
@@ -579,6 +598,12 @@ bool tc6_supported(const GemmParams& g) {
   // TMA: strides in bytes must be multiples of 16
   if ((g.a_map.stride_t * 4) % 16 != 0 || (g.a_map.stride_b * 4) % 16 != 0) return false;
   if (reinterpret_cast<uintptr_t>(g.A) % 16 != 0) return false;
+  // the epilogue reads and writes float4s: every row start must be 16-byte aligned
+  auto vec_ok = [](const void* ptr, const RowMap& m) {
+    return ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && m.stride_t % 4 == 0 && m.stride_b % 4 == 0);
+  };
+  if (!vec_ok(g.res, g.r_map) || !vec_ok(g.out_raw, g.o_map) || !vec_ok(g.out_act, g.e_map)) return false;
+  if (reinterpret_cast<uintptr_t>(g.bias) % 16 != 0 || reinterpret_cast<uintptr_t>(g.scale) % 16 != 0) return false;
   return true;
 }
 

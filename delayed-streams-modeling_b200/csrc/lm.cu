@@ -38,7 +38,13 @@ LmImpl::LmImpl(const dsm_lm_spec& sp, const dsm_weights* w, int dev, int batch) 
   hidden = sp.dim_feedforward == 4 * D ? 11 * D / 4 : 2 * sp.dim_feedforward / 3;   // batched_transformer.rs:153-157
   DSM_CHECK(hidden % 16 == 0, DSM_ERR_UNSUPPORTED, "gated hidden size %d must be a multiple of 16", hidden);
   DSM_CUDA(cudaSetDevice(device));
-  DSM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  {
+    // DSM_LM_PRIORITY=1: the LM branch is the longer one of the frame graph; let its CTAs win the SMs.
+    const char* e = getenv("DSM_LM_PRIORITY");
+    int lo = 0, hi = 0;
+    DSM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    DSM_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, (e && e[0] == '1') ? hi : (e && e[0] == '2') ? lo : 0));
+  }
   WeightTable wt(w);
   const bool random = (w == nullptr);
 

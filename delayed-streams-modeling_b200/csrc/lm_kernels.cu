@@ -149,9 +149,9 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
 }
 
 template <int D, int UNROLL>
-__global__ void __launch_bounds__(128) lm_attention_kernel(const __nv_bfloat16* __restrict__ q, RingState rs,
+__global__ void __launch_bounds__(128, 8) lm_attention_kernel(const __nv_bfloat16* __restrict__ q, RingState rs,
                                                             const uint8_t* __restrict__ mask, int H, int context,
-                                                            const __nv_bfloat16* __restrict__ k_ring,
+                                                            int n_items, const __nv_bfloat16* __restrict__ k_ring,
                                                             const __nv_bfloat16* __restrict__ v_ring,
                                                             __nv_bfloat16* __restrict__ out) {
   constexpr int LPK = D / 8;          // lanes per key
@@ -161,15 +161,18 @@ __global__ void __launch_bounds__(128) lm_attention_kernel(const __nv_bfloat16* 
   float* sc = sm;                     // [context] scores, then reused as [NW][D] partial outputs
   float* red = sm;
   __shared__ float s_red[NW];
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int HD = H * D;
+  // grid == n_items: one (stream, head) per CTA.  A smaller grid walks the items (persistent form: every
+  // CTA is resident at once, so a co-scheduled kernel with large CTAs is never starved of SM space).
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const int b = item / H, h = item % H;
   __nv_bfloat16* orow = out + (long long)b * HD + h * D;
   const bool active = mask ? mask[b] != 0 : true;
   if (!active) {
     // an inactive stream's output is never consumed (asr.rs:221-223); skip the ring read
     for (int d = tid; d < D; d += blockDim.x) orow[d] = __float2bfloat16_rn(0.f);
-    return;
+    continue;
   }
   const uint32_t p0 = rs.cur_pos[b];
   const int n = p0 + 1 < (uint32_t)context ? (int)(p0 + 1) : context;   // visible slots are [0, n)
@@ -272,6 +275,8 @@ __global__ void __launch_bounds__(128) lm_attention_kernel(const __nv_bfloat16* 
     const float v = (red[d] + red[D + d] + red[2 * D + d] + red[3 * D + d]) * inv;
     orow[d] = __float2bfloat16_rn(v);
   }
+  __syncthreads();                    // red[] is the next item's score buffer
+  }
 }
 
 void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint8_t* mask, int B, int H, int D,
@@ -291,10 +296,13 @@ void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint
     }
     carveout_set = true;
   }
+  static const int max_ctas = [] { const char* e = getenv("DSM_ATTN_CTAS"); return e ? atoi(e) : 0; }();
+  const int items = B * H;
+  const int grid = max_ctas > 0 ? std::min(items, max_ctas) : items;
   if (D == 128)
-    lm_attention_kernel<128, 8><<<B * H, 128, smem, st>>>(q, rs, mask, H, context, k_ring, v_ring, out);
+    lm_attention_kernel<128, 8><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
   else if (D == 64)
-    lm_attention_kernel<64, 8><<<B * H, 128, smem, st>>>(q, rs, mask, H, context, k_ring, v_ring, out);
+    lm_attention_kernel<64, 8><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
   else
     fail(DSM_ERR_UNSUPPORTED, "lm_attention: head_dim %d (64 or 128)", D);
   check_launch("lm_attention");

@@ -82,6 +82,13 @@ class AsrState:
                                          dtype=torch.int64)
         self.last_logits: Optional[torch.Tensor] = None
         self.last_tokens: Optional[torch.Tensor] = None
+        # Checker aid (not reference behaviour): tokens [B] sampled by the implementation under test for
+        # the step about to run.  Where such a token is a near-tie of the oracle's own argmax (logit gap
+        # <= tie_tol * max|logit|, i.e. inside the logits tolerance) the oracle follows it, so that one
+        # legitimate tie flip does not make every later frame incomparable.  `ties_followed` counts them.
+        self.follow_tokens: Optional[torch.Tensor] = None
+        self.tie_tol = 0.0
+        self.ties_followed = 0
 
     def step_pcm(self, pcm: torch.Tensor, mask=None, cond=None):
         # asr.rs:115-131
@@ -112,6 +119,14 @@ class AsrState:
                 pr = torch.softmax(torch.stack(heads, 0).float(), dim=-1)[:, :, 0, 0]
                 msgs.append(("step", self.model_step_idx, pr.clone()))
             tokens = logits[:, 0].argmax(dim=-1)
+            if self.follow_tokens is not None:
+                lg = logits[:, 0].float()
+                alt = torch.as_tensor(self.follow_tokens, dtype=torch.int64)
+                gap = lg.gather(1, tokens.view(b, 1)) - lg.gather(1, alt.view(b, 1))
+                near = (gap[:, 0] <= self.tie_tol * lg.abs().max()) & (alt != tokens) & tmask
+                self.ties_followed += int(near.sum())
+                tokens = torch.where(near, alt, tokens)
+                self.follow_tokens = None
             self.last_logits, self.last_tokens = logits[:, 0], tokens
             for bi, tok in enumerate(tokens.tolist()):
                 if not active[bi]:

@@ -40,6 +40,10 @@ def test_stt_1b_batch1_on_bundled_speech():
         oc = o_probe.encode_step(torch.from_numpy(fr).unsqueeze(1))[:, :, 0].numpy()
         same_codes += int((gc.astype(np.int64) == oc).all())
         gm = g.step_pcm(fr)
+        # Random-init logits over 8000 entries are nearly flat; a top-2 gap inside the logits tolerance may
+        # resolve either way (split-K atomics order, bf16 rounding).  The oracle then follows the device's
+        # choice so the remaining frames stay comparable; at most 2 such ties are accepted.
+        o.follow_tokens, o.tie_tol = g.last_tokens.astype(np.int64), 1e-2
         om = o.step_pcm(torch.from_numpy(fr).unsqueeze(1))
         worst = max(worst, rel_err(g.last_logits(), o.last_logits.numpy()))
         same_tok += int(g.last_tokens[0] == o.last_tokens.numpy()[0])
@@ -47,3 +51,4 @@ def test_stt_1b_batch1_on_bundled_speech():
     assert same_codes >= 0.995 * frames, f"RVQ codes identical on {same_codes}/{frames} frames"
     assert worst < 1e-2, f"logits rel err {worst:.3e}"
     assert same_tok == frames, f"greedy tokens identical on {same_tok}/{frames} frames"
+    assert o.ties_followed <= 2, f"{o.ties_followed} near-tie flips"
