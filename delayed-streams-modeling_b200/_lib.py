@@ -13,7 +13,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdsm_b200.so")
+LIB_PATH = os.environ.get("DSM_B200_LIB") or os.path.join(_HERE, "libdsm_b200.so")   # override: A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dsm_b200.h")
 
 DSM_F32, DSM_BF16, DSM_F16, DSM_U32 = 0, 1, 2, 3

@@ -9,6 +9,19 @@ namespace dsm {
 // ================================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp; the compiler then keeps tcgen05 / TMA operands in uniform registers instead of
+// wrapping every instruction in a lane-election loop (what `lane == 0` produces).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -144,7 +157,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   uint64_t* accum_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0), lane = threadIdx.x % 32;
   // weight-row tile: GATE -> gate rows [n0, n0+128) and value rows hidden + the same; otherwise NACC
   // consecutive 128-row tiles starting at n0
   const int n0 = blockIdx.x * TC_BN * (MODE == TC_GATE_BF16 ? 1 : NACC);
@@ -172,7 +185,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ---------------- TMA producer ----------------
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
@@ -185,7 +198,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       if (NACC == 2) tma_load_2d(st + A_BYTES, &map_w, kc, second, &full_bar[s]);
       tma_load_2d(st + NACC * A_BYTES, &map_x, kc, m0, &full_bar[s]);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc = make_idesc(BMX);
     for (int kb = 0; kb < num_kb; ++kb) {

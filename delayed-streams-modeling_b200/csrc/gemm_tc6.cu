@@ -6,13 +6,12 @@
 // from the CUDA cores (~45 TFLOP/s achieved) to the tensor pipe (2.25 PFLOP/s / 6).
 //
 //   warp 0 lane 0 : TMA of the f32 A tile (implicit-GEMM conv window: a 3-D box over [B, T_out, k*C_in]
-//                   with overlapping row stride) into a 128B-swizzled staging ring (3 slots)
-//   warp 3 lane 0 : TMA of the pre-split bf16 W planes (ring of 4-8 stages)
-//   warps 4-7     : converters -- a thread owns one tile row: reads it from staging, splits f32 -> 3 x bf16
-//                   and writes the three planes into TENSOR MEMORY with tcgen05.st (lane = row, 32 columns per
-//                   plane); the MMAs take A from TMEM, so shared memory only feeds W
+//                   with overlapping row stride) into a 128B-swizzled staging buffer
+//   warp 3 lane 0 : TMA of the pre-split bf16 W planes (ring of stages)
+//   warps 4-7     : converters -- read staging, split f32 -> 3 x bf16, write the three K-major 128B-
+//                   swizzled UMMA operand tiles, fence.proxy.async, signal the MMA warp
 //   warp 1 lane 0 : tcgen05.mma issuer: per k-block, for each of NJ column sub-tiles, 6 x 4 MMAs
-//   warp 2        : TMEM alloc / dealloc (columns [0,320) accumulators, [320,512) two A buffers)
+//   warp 2        : TMEM alloc / dealloc
 //   warps 8-15    : epilogue (tcgen05.ld -> bias / c2-dot / GELU / LayerScale / residual / ELU copy)
 #include "gemm_tc6.cuh"
 
@@ -23,6 +22,20 @@ namespace dsm {
 namespace {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// One lane of a converged warp.  Unlike `lane == 0`, the compiler knows the guarded region runs in a single
+// thread, so tcgen05.mma / TMA operands go straight to uniform registers; with `lane == 0` every tcgen05.mma was
+// wrapped in a lane-election loop (~100 cycles per instruction, 3x the 32-48 cycles an N=64 MMA executes in).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -48,6 +61,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
   asm volatile(
@@ -69,24 +83,17 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// A operand from tensor memory (lane = tile row, 32-bit column = two consecutive K elements), B from shared
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
-                                             uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
-               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -140,9 +147,7 @@ constexpr int T6_BM = 128;           // rows per CTA (UMMA M)
 constexpr int T6_BK = 64;            // K elements per k-block
 constexpr int T6_STG_SUB = T6_BM * 32 * 4;       // one staging sub-tile: 128 rows x 32 f32 (128-byte rows)
 constexpr int T6_STG = 2 * T6_STG_SUB;           // 32 KB per k-block
-constexpr int T6_NSTG = 3;                       // staging slots (TMA runs two k-blocks ahead of the converters)
-constexpr int T6_ACC_COLS = 320;                 // TMEM columns [0, 320): accumulators (one or two tile buffers)
-constexpr int T6_A_COLS = 96;                    // TMEM columns of one A buffer: 3 planes x 32 (64 bf16 per row)
+constexpr int T6_PLANE = T6_BM * T6_BK * 2;      // 16 KB per bf16 plane tile
 constexpr int T6_EPI_WARPS = 8;      // two per TMEM lane quadrant
 constexpr int T6_CVT_WARPS = 4;      // one converter thread per tile row
 constexpr int T6_THREADS = (4 + T6_CVT_WARPS + T6_EPI_WARPS) * 32;
@@ -161,7 +166,6 @@ struct Tc6Params {
   int nj;              // column sub-tiles per tile
   int pm;              // main-term accumulators the k-blocks rotate over (see the MMA issuer)
   int split_k;         // K splits per tile (work item = (tile, split)); partials meet in `ws`
-  int acc_bufs;        // accumulator tile buffers in TMEM (1 or 2)
   float* ws;           // [tiles * split_k][128][nj * BN] partial sums (split_k > 1)
   int* counters;       // [tiles] arrivals; the last split to arrive reduces in split order and stores
   const float* bias;
@@ -185,27 +189,27 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzle atoms need a 1024-byte aligned base
-  uint8_t* stg = smem;                           // [T6_NSTG][T6_STG]
-  uint8_t* wring = stg + T6_NSTG * T6_STG;       // [WS][W_STAGE]
+  uint8_t* stg = smem;                           // [2][T6_STG]
+  uint8_t* planes = stg + 2 * T6_STG;            // [2][3][T6_PLANE]
+  uint8_t* wring = planes + 2 * 3 * T6_PLANE;    // [WS][W_STAGE]
   float* scratch_all = reinterpret_cast<float*>(wring + WS * W_STAGE);   // [epilogue warps][16][36]
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + T6_EPI_WARPS * T6_SCR);
-  uint64_t* stg_full = bars;             // [T6_NSTG]
-  uint64_t* stg_empty = bars + 4;        // [T6_NSTG]
-  uint64_t* pl_full = bars + 8;          // [2]
-  uint64_t* pl_empty = bars + 10;        // [2]
-  uint64_t* acc_full = bars + 12;        // [2]
-  uint64_t* acc_empty = bars + 14;       // [2]
-  uint64_t* w_full = bars + 16;          // [WS]
+  uint64_t* stg_full = bars;             // [2]
+  uint64_t* stg_empty = bars + 2;        // [2]
+  uint64_t* pl_full = bars + 4;          // [2]
+  uint64_t* pl_empty = bars + 6;         // [2]
+  uint64_t* acc_full = bars + 8;         // [2]
+  uint64_t* acc_empty = bars + 10;       // [2]
+  uint64_t* w_full = bars + 12;          // [WS]
   uint64_t* w_empty = w_full + WS;       // [WS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + WS);
   uint32_t* last_flag = tmem_slot + 1;
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0), lane = threadIdx.x % 32;
   const int num_kb = (p.K + T6_BK - 1) / T6_BK;
   const int rows_box = p.t_sub * p.b_sub;
   const int acc_stride = p.nj * BN;          // columns of one accumulator set
-  const int buf_stride = (1 + p.pm) * acc_stride;   // columns of one tile's accumulators
-  const int AB = p.acc_bufs;                        // 2: the epilogue of tile i overlaps the MMAs of tile i+1
+  const int buf_stride = (1 + p.pm) * acc_stride;   // columns of one tile's accumulators (<= 256)
   const int total_tiles = p.m_tiles * p.n_groups;
   const int S = p.split_k;
   const int kb_per = (num_kb + S - 1) / S;       // the host picks S so that no split is empty
@@ -216,11 +220,9 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     tma_prefetch_desc(&map_w);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < T6_NSTG; ++s) {
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&stg_full[s], 1);
       mbar_init(&stg_empty[s], T6_CVT_WARPS);
-    }
-    for (int s = 0; s < 2; ++s) {
       mbar_init(&pl_full[s], T6_CVT_WARPS);
       mbar_init(&pl_empty[s], 1);
       mbar_init(&acc_full[s], 1);
@@ -238,7 +240,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     // ---------------- A producer: f32 conv-window tile -> staging ----------------
     int kit = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -246,8 +248,8 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int mt = tile / p.n_groups;
       const int t0 = (mt % p.t_tiles) * p.t_sub, b0 = (mt / p.t_tiles) * p.b_sub;
       for (int kb = kb0; kb < kb0 + kbn; ++kb, ++kit) {
-        const int s = kit % T6_NSTG;
-        mbar_wait(&stg_empty[s], ((kit / T6_NSTG) & 1) ^ 1);
+        const int s = kit & 1;
+        mbar_wait(&stg_empty[s], ((kit >> 1) & 1) ^ 1);
         const int kc = kb * T6_BK;
         const int nsub = (p.K - kc > 32) ? 2 : 1;
         mbar_expect_tx(&stg_full[s], (uint32_t)(nsub * rows_box * 128));
@@ -255,7 +257,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           tma_load_3d(stg + s * T6_STG + h * T6_STG_SUB, &map_a, kc + h * 32, t0, b0, &stg_full[s]);
       }
     }
-  } else if (warp == 3 && lane == 0) {
+  } else if (warp == 3 && elect_one()) {
     // ---------------- W producer: three bf16 planes per (k-block, column sub-tile) ----------------
     int wit = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -272,7 +274,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc = make_idesc(BN);
     // (a-plane, w-plane) pairs.  The tensor core truncates when it adds into the f32 accumulator, a
@@ -287,15 +289,15 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int pm = min(p.pm, kbn);                       // main accumulators actually written
       const int n0 = (tile % p.n_groups) * p.nj * BN;
       const int nj = min(p.nj, (p.N - n0 + BN - 1) / BN);
-      const int buf = li % AB;
-      mbar_wait(&acc_empty[buf], ((li / AB) & 1) ^ 1);     // epilogue has drained this TMEM buffer
+      const int buf = li & 1;
+      mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1);     // epilogue has drained this TMEM buffer
       tc_fence_after();
       const uint32_t acc_base = tmem_base + buf * buf_stride;
       for (int kb = 0; kb < kbn; ++kb, ++kit) {
         const int s = kit & 1;
         mbar_wait(&pl_full[s], (kit >> 1) & 1);
         tc_fence_after();
-        const uint32_t a_base = tmem_base + T6_ACC_COLS + s * T6_A_COLS;
+        const uint32_t a_base = smem_u32(planes + s * 3 * T6_PLANE);
         for (int j = 0; j < nj; ++j, ++wit) {
           const int ws = wit % WS;
           mbar_wait(&w_full[ws], (wit / WS) & 1);
@@ -303,14 +305,14 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const uint32_t w_base = smem_u32(wring + ws * W_STAGE);
 #pragma unroll
           for (int t = 0; t < 6; ++t) {
-            const uint32_t ta = a_base + pa[t] * 32;
+            const uint64_t da = make_smem_desc(a_base + pa[t] * T6_PLANE);
             const uint64_t dw = make_smem_desc(w_base + pw[t] * (BN * T6_BK * 2));
             const int set = t < 5 ? 0 : 1 + kb % pm;
             const bool first = t < 5 ? (kb == 0 && t == 0) : (kb < pm);
 #pragma unroll
             for (int k = 0; k < T6_BK / 16; ++k)
-              umma_bf16_ts(acc_base + set * acc_stride + j * BN, ta + k * 8, dw + (uint64_t)(k * 2), idesc,
-                           (first && k == 0) ? 0u : 1u);
+              umma_bf16(acc_base + set * acc_stride + j * BN, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc,
+                        (first && k == 0) ? 0u : 1u);
           }
           umma_commit(&w_empty[ws]);
         }
@@ -319,18 +321,15 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       umma_commit(&acc_full[buf]);
     }
   } else if (warp >= 4 && warp < 4 + T6_CVT_WARPS) {
-    // ---------------- converters: staging f32 -> three bf16 planes in tensor memory ----------------
-    // A thread owns tile row r = TMEM lane r (warps 4..7 reach lane quadrants 0..3): the A operand of the
-    // MMAs is read from TMEM, 32 columns (64 bf16) per plane and k-block.
-    const int r = (warp & 3) * 32 + lane;    // tile row
+    // ---------------- converters: staging f32 -> three swizzled bf16 operand tiles ----------------
+    const int r = (warp - 4) * 32 + lane;    // tile row
     const int sw = r & 7;
-    const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + T6_ACC_COLS;
     int kit = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int kb0 = (item % S) * kb_per, kbn = min(kb_per, num_kb - kb0);
       for (int kb = kb0; kb < kb0 + kbn; ++kb, ++kit) {
-        const int s = kit % T6_NSTG, ps = kit & 1;
-        const uint32_t ph = (kit / T6_NSTG) & 1, pph = (kit >> 1) & 1;
+        const int s = kit & 1;
+        const uint32_t ph = (kit >> 1) & 1;
         const bool have2 = p.K - kb * T6_BK > 32;      // second 32-wide half present
         float4 v[16];
         mbar_wait(&stg_full[s], ph);
@@ -344,13 +343,11 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&stg_empty[s]);      // staging slot may be refilled
-        mbar_wait(&pl_empty[ps], pph ^ 1);               // MMAs that read this plane buffer are done
-        tc_fence_after();
-        const uint32_t dst = a_lane + ps * T6_A_COLS;
+        mbar_wait(&pl_empty[s], ph ^ 1);                 // MMAs that read this plane buffer are done
+        uint8_t* dst = planes + s * 3 * T6_PLANE + r * 128;
         // Exact 3-way split by TRUNCATION: b1 = top 16 bits of x, r1 = x - b1 (exact), b2 = top 16 bits of
         // r1, r2 = r1 - b2 (exact), b3 = top 16 bits of r2 (r2 has <= 8 significant bits left, so b3 = r2).
         // No F2F conversions: one PRMT packs the upper halves of two floats into a bf16x2.
-        uint32_t h1[4], h2[4], h3[4];
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
           const float4 x0 = v[2 * cc], x1 = v[2 * cc + 1];
@@ -367,23 +364,14 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const float s0 = r0 - __uint_as_float(v0 & 0xffff0000u), s1 = r1 - __uint_as_float(v1 & 0xffff0000u);
             p3[e] = __byte_perm(__float_as_uint(s0), __float_as_uint(s1), 0x7632);
           }
-          if (cc & 1) {
-            // eight floats per cc -> four packed columns per plane; store eight columns at a time
-            uint32_t q1[8] = {h1[0], h1[1], h1[2], h1[3], p1[0], p1[1], p1[2], p1[3]};
-            uint32_t q2[8] = {h2[0], h2[1], h2[2], h2[3], p2[0], p2[1], p2[2], p2[3]};
-            uint32_t q3[8] = {h3[0], h3[1], h3[2], h3[3], p3[0], p3[1], p3[2], p3[3]};
-            tmem_st8(dst + (cc - 1) * 4, q1);
-            tmem_st8(dst + 32 + (cc - 1) * 4, q2);
-            tmem_st8(dst + 64 + (cc - 1) * 4, q3);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h1[e] = p1[e], h2[e] = p2[e], h3[e] = p3[e];
-          }
+          const int chunk = (cc ^ sw) << 4;
+          *reinterpret_cast<uint4*>(dst + chunk) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+          *reinterpret_cast<uint4*>(dst + T6_PLANE + chunk) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+          *reinterpret_cast<uint4*>(dst + 2 * T6_PLANE + chunk) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
         }
-        tmem_st_wait();
-        tc_fence_before();
+        fence_proxy_async();      // make the generic-proxy stores visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&pl_full[ps]);
+        if (lane == 0) mbar_arrive(&pl_full[s]);
       }
     }
   } else if (warp >= 4 + T6_CVT_WARPS) {
@@ -415,8 +403,8 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const uint32_t raw_off = p.out_raw ? (uint32_t)p.o_map.off(m) : 0u;
       const uint32_t act_off = p.out_act ? (uint32_t)p.e_map.off(m) : 0u;
       const uint32_t ok_mask = __ballot_sync(0xffffffffu, row_ok);
-      const int buf = li % AB;
-      mbar_wait(&acc_full[buf], (li / AB) & 1);
+      const int buf = li & 1;
+      mbar_wait(&acc_full[buf], (li >> 1) & 1);
       tc_fence_after();
       const uint32_t acc_addr = lane_addr + buf * buf_stride;
       const int n_chunks = nj * BN / 32;
@@ -585,11 +573,11 @@ static EncodeTiledFn encode_tiled6() {
 template <int BN>
 struct T6Cfg {
   static constexpr int W_STAGE = 3 * BN * T6_BK * 2;
-  static constexpr int FIXED = T6_NSTG * T6_STG;                          // 96 KB of f32 staging
+  static constexpr int FIXED = 2 * T6_STG + 2 * 3 * T6_PLANE;             // 160 KB
+  static constexpr int WS_RAW = (209 * 1024 - FIXED) / W_STAGE;
+  static constexpr int WS = WS_RAW > 4 ? 4 : WS_RAW;
   static constexpr int SCRATCH = T6_EPI_WARPS * T6_SCR * 4;
-  static constexpr int WS_RAW = (232448 - 1024 - FIXED - SCRATCH) / W_STAGE;
-  static constexpr int WS = WS_RAW > 8 ? 8 : WS_RAW;
-  static constexpr int SMEM = FIXED + WS * W_STAGE + SCRATCH + (16 + 2 * WS) * 8 + 16;   // barriers + tmem slot + last flag
+  static constexpr int SMEM = FIXED + WS * W_STAGE + SCRATCH + (12 + 2 * WS) * 8 + 16;   // barriers + tmem slot + last flag
   static_assert(SMEM <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static_assert(WS >= 2, "need at least two W stages");
 };
@@ -608,7 +596,7 @@ static void launch6(const Tc6Gemm& g, cudaStream_t st) {
   p.t_tiles = ceil_div(g.T_out, g.t_sub), p.nj = g.nj, p.pm = g.pm;
   p.m_tiles = p.t_tiles * ceil_div(g.B, g.b_sub);
   p.n_groups = ceil_div(g.N, g.nj * BN);
-  p.split_k = g.split_k, p.ws = g.ws, p.counters = g.counters, p.acc_bufs = g.acc_bufs;
+  p.split_k = g.split_k, p.ws = g.ws, p.counters = g.counters;
   p.bias = g.ep.bias, p.neg = g.ep.neg, p.scale = g.ep.scale, p.res = g.ep.res, p.r_map = g.ep.r_map, p.act = g.ep.act;
   p.out_raw = g.ep.out_raw, p.o_map = g.ep.o_map, p.out_act = g.ep.out_act, p.e_map = g.ep.e_map;
   const long long tiles = (long long)p.m_tiles * p.n_groups * g.split_k;
@@ -681,19 +669,10 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes,
   // column sub-tiles per CTA: as many as TMEM holds (512 columns) while the grid still covers the SMs
   // (TMEM: two tile buffers of 256 columns, each shared by the correction accumulator and >= 1 main
   // accumulator => at most 128 output columns per tile)
-  static const int max_tile_n = [] { const char* e = getenv("DSM_TC6_TILE_N"); int v = e ? atoi(e) : 0; return v >= 32 ? v : 64; }();
-  int nj = std::max(1, std::min(n_sub, std::min(128, max_tile_n) / t.bn));
+  int nj = std::min(n_sub, 128 / t.bn);
   while (nj > 1 && m_tiles * ceil_div(n_sub, nj) < 148) nj = (nj + 1) / 2;
   t.nj = nj;
-  // TMEM: 320 accumulator columns (the other 192 hold two A buffers).  Two tile buffers when they fit with
-  // at least one main accumulator beside the correction accumulator, else one.
-  // The tensor core truncates when it accumulates, so long K loops rotate the dominant term over several
-  // accumulators (pm); beyond 8 k-blocks that takes the whole accumulator region (one tile buffer: the
-  // epilogue of a tile then no longer overlaps the next tile's MMAs, a small share of a long K loop).
-  const int tile_n = nj * t.bn;
-  const bool long_k = ceil_div(g.K, T6_BK) > 8;
-  t.acc_bufs = (!long_k && 2 * 2 * tile_n <= T6_ACC_COLS) ? 2 : 1;
-  t.pm = std::max(1, std::min(7, T6_ACC_COLS / (t.acc_bufs * tile_n) - 1));
+  t.pm = std::max(1, std::min(7, 256 / (nj * t.bn) - 1));
   // Skinny problems (few tiles, long K) cannot fill 148 SMs with tiles alone: split K over several CTAs
   // per tile; the partial sums meet in the shared workspace and the last arrival reduces them in order.
   {
