@@ -183,7 +183,7 @@ struct Tc6Params {
 // Persistent: gridDim.x CTAs (<= one per SM) walk the tiles; TMEM holds two accumulator buffers so the
 // epilogue warps drain tile i while the producers / converters / MMA issuer are already on tile i+1.
 template <int BN, int WS>
-__global__ void __maxnreg__(96)   // 512 x 96 registers leave room for two attention CTAs on the same SM
+__global__ void __maxnreg__(128)   // 512 x 128 = the whole register file: one CTA per SM anyway (218 KB of shared memory)
 tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Tc6Params p) {
   constexpr int W_STAGE = 3 * BN * T6_BK * 2;   // three bf16 planes of a BN x 64 tile
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -412,6 +412,21 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int qrow = lane >> 3, cs = lane & 7;   // 8 lanes per row: 8 x float4 = one 128-byte segment
 #pragma unroll 1
       for (int c = split_rows ? 0 : sib; c < n_chunks; c += split_rows ? 1 : 2) {
+        // The residual rows of this chunk are requested first (8 float4 per thread), so that their HBM round trip
+        // overlaps the TMEM loads and the transposition instead of following them.
+        const int col = n0 + c * 32 + cs * 4;
+        const bool col_ok = col < p.N;              // N is a multiple of 32: a chunk is valid as a whole
+        float4 rres[2][4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int rr = half * 16 + 4 * q + qrow;
+            const uint32_t ro = __shfl_sync(0xffffffffu, res_off, rr);
+            const bool want = p.res && col_ok && ((ok_mask >> rr) & 1u) && !(split_rows && half != sib) && S == 1;
+            rres[half][q] = want ? __ldg(reinterpret_cast<const float4*>(p.res + ro + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         float v[32];
         tmem_ld32(acc_addr + c * 32, v);
         for (int a = 1; a <= pm; ++a) {
@@ -427,8 +442,6 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // 16 TMEM rows park them as float4s in a [16][36] scratch tile, then all 32 lanes sweep it four
         // rows per instruction (8 lanes x 16 B = one full 128-byte row segment), so every global access
         // of the epilogue is a float4 in a fully used line.
-        const int col = n0 + c * 32 + cs * 4;
-        const bool col_ok = col < p.N;              // N is a multiple of 32: a chunk is valid as a whole
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), scale4 = make_float4(1.f, 1.f, 1.f, 1.f);
         if (p.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         if (p.scale && col_ok) scale4 = __ldg(reinterpret_cast<const float4*>(p.scale + col));
@@ -452,33 +465,23 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             __syncwarp();
             continue;
           }
-          float4 rres[4];
-          uint32_t wo[4], ao[4];
-          bool ok[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int rr = half * 16 + 4 * q + qrow;
-            const uint32_t ro = __shfl_sync(0xffffffffu, res_off, rr);
-            wo[q] = __shfl_sync(0xffffffffu, raw_off, rr);
-            ao[q] = __shfl_sync(0xffffffffu, act_off, rr);
-            ok[q] = col_ok && ((ok_mask >> rr) & 1u);
-            rres[q] = (p.res && ok[q]) ? __ldg(reinterpret_cast<const float4*>(p.res + ro + col))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (!ok[q]) continue;
+            const uint32_t wo = __shfl_sync(0xffffffffu, raw_off, rr);
+            const uint32_t ao = __shfl_sync(0xffffffffu, act_off, rr);
+            if (!(col_ok && ((ok_mask >> rr) & 1u))) continue;
             float4 x = *reinterpret_cast<const float4*>(scratch + (4 * q + qrow) * T6_SCR_LD + cs * 4);
             if (p.bias) {
               if (p.neg) x.x = bias4.x - x.x, x.y = bias4.y - x.y, x.z = bias4.z - x.z, x.w = bias4.w - x.w;
               else x.x += bias4.x, x.y += bias4.y, x.z += bias4.z, x.w += bias4.w;
             }
             if (p.act == 1) x.x = gelu_erf(x.x), x.y = gelu_erf(x.y), x.z = gelu_erf(x.z), x.w = gelu_erf(x.w);
-            x.x = x.x * scale4.x + rres[q].x, x.y = x.y * scale4.y + rres[q].y;
-            x.z = x.z * scale4.z + rres[q].z, x.w = x.w * scale4.w + rres[q].w;
-            if (p.out_raw) *reinterpret_cast<float4*>(p.out_raw + wo[q] + col) = x;
+            x.x = x.x * scale4.x + rres[half][q].x, x.y = x.y * scale4.y + rres[half][q].y;
+            x.z = x.z * scale4.z + rres[half][q].z, x.w = x.w * scale4.w + rres[half][q].w;
+            if (p.out_raw) *reinterpret_cast<float4*>(p.out_raw + wo + col) = x;
             if (p.out_act)
-              *reinterpret_cast<float4*>(p.out_act + ao[q] + col) =
+              *reinterpret_cast<float4*>(p.out_act + ao + col) =
                   make_float4(elu_ref(x.x), elu_ref(x.y), elu_ref(x.z), elu_ref(x.w));
           }
           __syncwarp();

@@ -147,8 +147,22 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
                : "l"(p));
   return r;
 }
+// Same, with an L2 evict-first policy: 25 GB of KV rings stream through the 126 MB L2 every step and would
+// otherwise evict the codec's weights and activations that the concurrent Mimi branch re-reads.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ld_stream16(const void* p, uint64_t pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
 
-template <int D, int UNROLL>
+template <int D, int UNROLL, bool EVICT>
 __global__ void __launch_bounds__(128, 8) lm_attention_kernel(const __nv_bfloat16* __restrict__ q, RingState rs,
                                                             const uint8_t* __restrict__ mask, int H, int context,
                                                             int n_items, const __nv_bfloat16* __restrict__ k_ring,
@@ -163,6 +177,7 @@ __global__ void __launch_bounds__(128, 8) lm_attention_kernel(const __nv_bfloat1
   __shared__ float s_red[NW];
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int HD = H * D;
+  const uint64_t pol = EVICT ? l2_evict_first_policy() : 0;
   // grid == n_items: one (stream, head) per CTA.  A smaller grid walks the items (persistent form: every
   // CTA is resident at once, so a co-scheduled kernel with large CTAs is never starved of SM space).
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -194,7 +209,7 @@ __global__ void __launch_bounds__(128, 8) lm_attention_kernel(const __nv_bfloat1
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const int j = j0 + u * KPW + sub;
-      kv[u] = j < n ? ld_stream16(kb + (long long)j * D + c8 * 8) : make_uint4(0, 0, 0, 0);
+      kv[u] = j < n ? (EVICT ? ld_stream16(kb + (long long)j * D + c8 * 8, pol) : ld_stream16(kb + (long long)j * D + c8 * 8)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -244,7 +259,7 @@ __global__ void __launch_bounds__(128, 8) lm_attention_kernel(const __nv_bfloat1
     for (int u = 0; u < UNROLL; ++u) {
       const int j = j0 + u * KPW + sub;
       const bool ok = j < n;
-      vv[u] = ok ? ld_stream16(vb + (long long)j * D + c8 * 8) : make_uint4(0, 0, 0, 0);
+      vv[u] = ok ? (EVICT ? ld_stream16(vb + (long long)j * D + c8 * 8, pol) : ld_stream16(vb + (long long)j * D + c8 * 8)) : make_uint4(0, 0, 0, 0);
       pj[u] = ok ? sc[j] : 0.f;
     }
 #pragma unroll
@@ -289,20 +304,25 @@ void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint
   if (!carveout_set) {
     const char* e = getenv("DSM_ATTN_CARVEOUT");
     if (e && e[0] == '1') {
-      DSM_CUDA(cudaFuncSetAttribute(lm_attention_kernel<128, 8>, cudaFuncAttributePreferredSharedMemoryCarveout,
+      DSM_CUDA(cudaFuncSetAttribute(lm_attention_kernel<128, 8, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
-      DSM_CUDA(cudaFuncSetAttribute(lm_attention_kernel<64, 8>, cudaFuncAttributePreferredSharedMemoryCarveout,
+      DSM_CUDA(cudaFuncSetAttribute(lm_attention_kernel<64, 8, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
     }
     carveout_set = true;
   }
   static const int max_ctas = [] { const char* e = getenv("DSM_ATTN_CTAS"); return e ? atoi(e) : 0; }();
+  static const int evict = [] { const char* e = getenv("DSM_ATTN_EVICT_FIRST"); return e ? atoi(e) : 0; }();
   const int items = B * H;
   const int grid = max_ctas > 0 ? std::min(items, max_ctas) : items;
-  if (D == 128)
-    lm_attention_kernel<128, 8><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
+  if (D == 128 && evict)
+    lm_attention_kernel<128, 8, true><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
+  else if (D == 128)
+    lm_attention_kernel<128, 8, false><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
+  else if (D == 64 && evict)
+    lm_attention_kernel<64, 8, true><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
   else if (D == 64)
-    lm_attention_kernel<64, 8><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
+    lm_attention_kernel<64, 8, false><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
   else
     fail(DSM_ERR_UNSUPPORTED, "lm_attention: head_dim %d (64 or 128)", D);
   check_launch("lm_attention");
