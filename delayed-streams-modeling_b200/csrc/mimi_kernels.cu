@@ -322,22 +322,15 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
   const float* kb = k_ring + ((long long)b * H + h) * context * D;
   const float* vb = v_ring + ((long long)b * H + h) * context * D;
 
-  // slot position as kv_cache.rs:199-214 reconstructs it, then overridden for the slots written this step
-  auto slot_pos = [&](int j) -> long long {
-    long long pj;
-    if (p0 < context) pj = j < p0 ? j : (1LL << 40);
-    else {
-      const long long off = p0 - i0;
-      pj = j < i0 ? j + off : j + off - context;
-    }
-    for (int s = 0; s < t; ++s)
-      if (j == (i0 + s) % context) pj = p0 + s;
-    return pj;
-  };
-
-  // 4 warps x 2 keys x UNR keys in flight per iteration: the loads are issued together (memory-level
-  // parallelism), then reduced
+  // Scores.  4 warps x 2 keys x UNR keys in flight per iteration; 16 lanes share a key (one float4 each), so
+  // every iteration leaves 2*UNR partial dot products per lane that must be summed over 16 lanes.  They are
+  // reduced together: at each butterfly step a lane keeps half of its values and hands the other half to its
+  // partner (8 shuffles per iteration instead of 32; the pairing order 8,4,2,1 and therefore the rounding are
+  // those of a plain xor-shuffle tree).  The visibility mask is applied later, once per score.
   constexpr int UNR = 4;
+  static_assert(TQ == 2 && UNR == 4, "the multi-value reduction below is written for 8 values per lane");
+  const bool h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+  const int my_u = (h8 ? 2 : 0) + (h4 ? 1 : 0), my_s = h2 ? 1 : 0;   // the (key, query) this lane ends up with
   for (int j0 = warp * 2 * UNR; j0 < context; j0 += 8 * UNR) {
     float4 kv[UNR];
 #pragma unroll
@@ -346,35 +339,53 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
       kv[u] = j < context ? __ldg(reinterpret_cast<const float4*>(kb + (long long)j * D + c4 * 4))
                           : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    float v8[8];   // index u * 2 + s
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int j = j0 + 2 * u + sub;
-      float part[TQ];
+    for (int u = 0; u < UNR; ++u)
 #pragma unroll
-      for (int s = 0; s < TQ; ++s) {
-        part[s] = q[s].x * kv[u].x + q[s].y * kv[u].y + q[s].z * kv[u].z + q[s].w * kv[u].w;
+      for (int s = 0; s < TQ; ++s)
+        v8[u * 2 + s] = q[s].x * kv[u].x + q[s].y * kv[u].y + q[s].z * kv[u].z + q[s].w * kv[u].w;
+    float v4[4], v2[2];
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) part[s] += __shfl_xor_sync(0xffffffffu, part[s], o);
-      }
-      if (c4 == 0 && j < context) {
-        const long long pj = active ? slot_pos(j) : 0;
-#pragma unroll
-        for (int s = 0; s < TQ; ++s) {
-          if (s < t) {
-            const bool vis = !active || pj <= p0 + s;
-            sc[s * context + j] = vis ? part[s] * scale : -INFINITY;
-          }
-        }
-      }
+    for (int i = 0; i < 4; ++i) {
+      const float recv = __shfl_xor_sync(0xffffffffu, h8 ? v8[i] : v8[i + 4], 8);
+      v4[i] = (h8 ? v8[i + 4] : v8[i]) + recv;
     }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float recv = __shfl_xor_sync(0xffffffffu, h4 ? v4[i] : v4[i + 2], 4);
+      v2[i] = (h4 ? v4[i + 2] : v4[i]) + recv;
+    }
+    float v1 = (h2 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? v2[0] : v2[1], 2);
+    v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+    const int j = j0 + 2 * my_u + sub;
+    if ((lane & 1) == 0 && j < context && my_s < t) sc[my_s * context + j] = v1 * scale;
   }
   __syncthreads();
 
-  // softmax: warp s normalises query s
+  // mask + softmax: warp s normalises query s.  Slot positions as kv_cache.rs:199-214 reconstructs them,
+  // overridden for the slots written this step.
   if (warp < t) {
     float* row = sc + warp * context;
+    const long long off = p0 - i0;
+    auto visible = [&](int j) -> bool {
+      if (!active) return true;
+      long long pj;
+      if (p0 < context) pj = j < p0 ? j : (1LL << 40);
+      else pj = j < i0 ? j + off : j + off - context;
+      for (int s = 0; s < t; ++s) {
+        int ws = i0 + s;
+        if (ws >= context) ws -= context;
+        if (j == ws) pj = p0 + s;
+      }
+      return pj <= p0 + warp;
+    };
     float mx = -INFINITY;
-    for (int j = lane; j < context; j += 32) mx = fmaxf(mx, row[j]);
+    for (int j = lane; j < context; j += 32) {
+      const float x = visible(j) ? row[j] : -INFINITY;
+      row[j] = x;
+      mx = fmaxf(mx, x);
+    }
     mx = warp_max(mx);
     float sum = 0.f;
     for (int j = lane; j < context; j += 32) {
