@@ -118,6 +118,30 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle on the host cores
 # ---------------------------------------------------------------------------------------------
+def ncu_attention_traffic(B, lspec):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of lm_attention_kernel, from the committed
+    `ncu --set full` capture (profiles/r01_attn_set_full_raw.csv: stt-1b, 256 streams, full rings).  None when
+    the capture does not describe this configuration."""
+    import csv
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_attn_set_full_raw.csv")
+    if not os.path.exists(path) or (B, lspec.num_heads, lspec.head_dim, lspec.context) != (256, 16, 128, 750):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        rows = list(csv.reader(open(path)))
+        ix = {n: i for i, n in enumerate(rows[0])}
+        tot, n = 0.0, 0
+        for r in rows[2:]:
+            if "lm_attention_kernel" not in r[ix["Kernel Name"]] or int(r[ix["launch__grid_size"]]) != B * lspec.num_heads:
+                continue
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(r[ix[k]]) * scale[rows[1][ix[k]]]
+            n += 1
+        return tot / n if n else None
+    except Exception:
+        return None
+
+
 def oracle_throughput(workload: str, streams: int, steps: int, warmup: int):
     """Times oracle steps (PyTorch CPU f32 restatement of the reference's candle CPU path) on a bounded
     sample: `streams` streams of the same architecture.  Returns (frames_per_s, ms_per_step, cores)."""
@@ -339,7 +363,7 @@ def run_ours(args):
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
         step_ms = ms_dev / args.steps
         roofline = {"bound": "hbm", "kernel": "lm_attention_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": ncu_attention_traffic(B, lspec), "peak_source": peak_src,
                     "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_timed": n_launch,
                     "launches_per_step": lspec.num_layers,
                     "share_of_step": avg_ms * lspec.num_layers / step_ms,
