@@ -672,7 +672,8 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes,
   // column sub-tiles per CTA: as many as TMEM holds (512 columns) while the grid still covers the SMs
   // (TMEM: two tile buffers of 256 columns, each shared by the correction accumulator and >= 1 main
   // accumulator => at most 128 output columns per tile)
-  int nj = std::min(n_sub, 128 / t.bn);
+  static const int max_tile_n = [] { const char* e = getenv("DSM_TC6_TILE_N"); int v = e ? atoi(e) : 0; return v >= 32 ? v : 128; }();
+  int nj = std::max(1, std::min(n_sub, std::min(128, max_tile_n) / t.bn));
   while (nj > 1 && m_tiles * ceil_div(n_sub, nj) < 148) nj = (nj + 1) / 2;
   t.nj = nj;
   t.pm = std::max(1, std::min(7, 256 / (nj * t.bn) - 1));
