@@ -159,7 +159,31 @@ dsm_status dsm_debug_gemm_f32(int32_t impl, int32_t B, int32_t T, int64_t stride
     g.A = dA, g.a_map = RowMap{T, (long long)stride_b, (long long)stride_t}, g.M = B * T, g.N = N, g.K = K;
     g.out_raw = dO, g.o_map = dense_rows(1, N);
     if (bias) g.bias = a.upload(std::vector<float>(bias, bias + N));
-    if (impl == 1) {
+    __nv_bfloat16* dOP = nullptr;
+    if (impl == 2 || impl == 3) {
+      // A handed over as three bf16 planes (exact truncation split, as the producers of the codec do it)
+      std::vector<uint16_t> pl((size_t)3 * a_elems);
+      for (int64_t i = 0; i < a_elems; ++i) {
+        float x = A[i];
+        for (int q = 0; q < 3; ++q) {
+          uint32_t u;
+          memcpy(&u, &x, 4);
+          u &= 0xffff0000u;
+          float hi;
+          memcpy(&hi, &u, 4);
+          pl[(size_t)q * a_elems + i] = (uint16_t)(u >> 16);
+          x -= hi;
+        }
+      }
+      __nv_bfloat16* dP = a.alloc<__nv_bfloat16>(pl.size());
+      DSM_CUDA(cudaMemcpy(dP, pl.data(), pl.size() * 2, cudaMemcpyHostToDevice));
+      g.a_planes = dP, g.a_plane_stride = a_elems;
+      if (impl == 3) {
+        dOP = a.alloc<__nv_bfloat16>((size_t)3 * B * T * N);
+        g.out_planes = dOP, g.p_map = dense_rows(1, N), g.out_plane_stride = (long long)B * T * N;
+      }
+    }
+    if (impl >= 1) {
       DSM_CHECK(tc6_supported(g), DSM_ERR_UNSUPPORTED, "shape not supported by the tensor-core codec GEMM");
       Tc6Gemm t;
       tc6_prepare(t, g, tc6_split_weights(a, hw, N, K), tc6_make_workspace(a));
@@ -170,6 +194,23 @@ dsm_status dsm_debug_gemm_f32(int32_t impl, int32_t B, int32_t T, int64_t stride
     }
     DSM_CUDA(cudaDeviceSynchronize());
     DSM_CUDA(cudaMemcpy(out, dO, (size_t)B * T * N * 4, cudaMemcpyDeviceToHost));
+    if (impl == 3) {
+      // return the sum of the stored planes: must reproduce the f32 result bit for bit
+      const size_t n = (size_t)B * T * N;
+      std::vector<uint16_t> pl(3 * n);
+      DSM_CUDA(cudaMemcpy(pl.data(), dOP, pl.size() * 2, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < n; ++i) {
+        float acc = 0.f;
+        for (int q = 0; q < 3; ++q) {
+          uint32_t u = (uint32_t)pl[q * n + i] << 16;
+          float f;
+          memcpy(&f, &u, 4);
+          acc += f;
+        }
+        DSM_CHECK(memcmp(&acc, &out[i], 4) == 0 || (acc != acc && out[i] != out[i]), DSM_ERR_CUDA,
+                  "plane sum differs from the f32 result at %zu", i);
+      }
+    }
   });
 }
 

@@ -92,4 +92,26 @@ __device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
+// Exact 3-way split of an f32 by truncation: x = h + m + l with bf16 h, m, l (8 + 8 + 8 significant bits).  The
+// tcgen05 codec GEMM takes activations in this form (gemm_tc6.cu); producers that feed its skinny GEMMs store it.
+__device__ __forceinline__ void split3_bf16(float x, uint16_t& h, uint16_t& m, uint16_t& l) {
+  const uint32_t u = __float_as_uint(x);
+  h = (uint16_t)(u >> 16);
+  const float r1 = x - __uint_as_float(u & 0xffff0000u);
+  const uint32_t v = __float_as_uint(r1);
+  m = (uint16_t)(v >> 16);
+  const float r2 = r1 - __uint_as_float(v & 0xffff0000u);
+  l = (uint16_t)(__float_as_uint(r2) >> 16);
+}
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* base, long long plane_stride, long long off, const float4& x) {
+  uint16_t h[4], m[4], l[4];
+  split3_bf16(x.x, h[0], m[0], l[0]);
+  split3_bf16(x.y, h[1], m[1], l[1]);
+  split3_bf16(x.z, h[2], m[2], l[2]);
+  split3_bf16(x.w, h[3], m[3], l[3]);
+  *reinterpret_cast<uint2*>(base + off) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+  *reinterpret_cast<uint2*>(base + plane_stride + off) = make_uint2(m[0] | ((uint32_t)m[1] << 16), m[2] | ((uint32_t)m[3] << 16));
+  *reinterpret_cast<uint2*>(base + 2 * plane_stride + off) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+}
+
 }  // namespace dsm

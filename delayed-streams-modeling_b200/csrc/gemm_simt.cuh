@@ -32,6 +32,14 @@ struct GemmParams {
   RowMap e_map{1, 0, 0};
   __nv_bfloat16* out_bf16 = nullptr;
   RowMap h_map{1, 0, 0};
+  // tcgen05 codec GEMM only (gemm_tc6): operands pre-split into three bf16 planes, x = p0 + p1 + p2 exactly.
+  // a_planes: A as planes (plane q at a_planes + q * a_plane_stride, rows addressed by a_map in elements); the
+  // f32 A is then not read.  out_planes: the result additionally stored as planes for the next GEMM.
+  const __nv_bfloat16* a_planes = nullptr;
+  long long a_plane_stride = 0;
+  __nv_bfloat16* out_planes = nullptr;
+  RowMap p_map{1, 0, 0};
+  long long out_plane_stride = 0;
 };
 
 template <typename T>

@@ -70,6 +70,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -127,6 +134,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// Exact 3-way split of four floats by truncation (see the converter warps): x = h + m + l with bf16 h, m, l.
+__device__ __forceinline__ void split3_x4(const float4& x, uint2& h, uint2& m, uint2& l) {
+  const float xs[4] = {x.x, x.y, x.z, x.w};
+  uint32_t hh[2], mm[2], ll[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const float a0 = xs[2 * e], a1 = xs[2 * e + 1];
+    const uint32_t u0 = __float_as_uint(a0), u1 = __float_as_uint(a1);
+    hh[e] = __byte_perm(u0, u1, 0x7632);
+    const float r0 = a0 - __uint_as_float(u0 & 0xffff0000u), r1 = a1 - __uint_as_float(u1 & 0xffff0000u);
+    const uint32_t v0 = __float_as_uint(r0), v1 = __float_as_uint(r1);
+    mm[e] = __byte_perm(v0, v1, 0x7632);
+    const float s0 = r0 - __uint_as_float(v0 & 0xffff0000u), s1 = r1 - __uint_as_float(v1 & 0xffff0000u);
+    ll[e] = __byte_perm(__float_as_uint(s0), __float_as_uint(s1), 0x7632);
+  }
+  h = make_uint2(hh[0], hh[1]), m = make_uint2(mm[0], mm[1]), l = make_uint2(ll[0], ll[1]);
+}
 // ELU as the reference computes it: exp(x) - 1 for x <= 0 (candle Activation::Elu), not expm1
 __device__ __forceinline__ float elu_ref(float x) { return x > 0.f ? x : expf(x) - 1.f; }
 // K-major SWIZZLE_128B tile with 128-byte rows (see gemm_tc.cu)
@@ -151,8 +175,10 @@ constexpr int T6_PLANE = T6_BM * T6_BK * 2;      // 16 KB per bf16 plane tile
 constexpr int T6_EPI_WARPS = 8;      // two per TMEM lane quadrant
 constexpr int T6_CVT_WARPS = 4;      // one converter thread per tile row
 constexpr int T6_THREADS = (4 + T6_CVT_WARPS + T6_EPI_WARPS) * 32;
+// Minimum spacing of the 4-MMA issue groups (see the MMA issuer), overridable for A/B runs (DSM_TC6_PACE64/32)
+constexpr int T6_GROUP_CYCLES_64 = 128, T6_GROUP_CYCLES_32 = 176;
+constexpr int T6_NPL_PRE = 3;        // operand-plane buffers of the pre-split variant (48 KB each)
 constexpr int T6_SCR_LD = 36;        // floats per scratch row: 32 columns + 4 (float4 rows stay conflict-free)
-constexpr int T6_SCR = 16 * T6_SCR_LD;   // floats of one epilogue warp's transposition tile
 
 }  // namespace
 
@@ -166,6 +192,7 @@ struct Tc6Params {
   int nj;              // column sub-tiles per tile
   int pm;              // main-term accumulators the k-blocks rotate over (see the MMA issuer)
   int split_k;         // K splits per tile (work item = (tile, split)); partials meet in `ws`
+  int pace;            // minimum cycles between 4-MMA issue groups
   float* ws;           // [tiles * split_k][128][nj * BN] partial sums (split_k > 1)
   int* counters;       // [tiles] arrivals; the last split to arrive reduces in split order and stores
   const float* bias;
@@ -178,29 +205,39 @@ struct Tc6Params {
   RowMap o_map;
   float* out_act;
   RowMap e_map;
+  __nv_bfloat16* out_pl;   // optional: the result as three bf16 planes (plane q at out_pl + q * pl_stride)
+  RowMap pl_map;
+  long long pl_stride;
 };
 
 // Persistent: gridDim.x CTAs (<= one per SM) walk the tiles; TMEM holds two accumulator buffers so the
 // epilogue warps drain tile i while the producers / converters / MMA issuer are already on tile i+1.
-template <int BN, int WS>
+// PRE: the A operand arrives already split (bf16 planes [3][rows][K] written by the producer of the activation:
+// LayerNorm, attention, a GELU epilogue, the RVQ residual update), so the A tile goes from TMA straight into the
+// swizzled operand buffers -- no f32 staging, no converter hop, and the freed 64 KB make the operand ring NPL deep.
+// This is the form the codec's skinny GEMMs take (512 or 256 rows: one tile per CTA, latency-bound K loops).
+template <int BN, int WS, bool PRE>
 __global__ void __maxnreg__(128)   // 512 x 128 = the whole register file: one CTA per SM anyway (218 KB of shared memory)
 tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const Tc6Params p) {
   constexpr int W_STAGE = 3 * BN * T6_BK * 2;   // three bf16 planes of a BN x 64 tile
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzle atoms need a 1024-byte aligned base
-  uint8_t* stg = smem;                           // [2][T6_STG]
-  uint8_t* planes = stg + 2 * T6_STG;            // [2][3][T6_PLANE]
-  uint8_t* wring = planes + 2 * 3 * T6_PLANE;    // [WS][W_STAGE]
-  float* scratch_all = reinterpret_cast<float*>(wring + WS * W_STAGE);   // [epilogue warps][16][36]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + T6_EPI_WARPS * T6_SCR);
+  constexpr int NPL = PRE ? T6_NPL_PRE : 2;      // operand-plane buffers
+  uint8_t* stg = smem;                           // [2][T6_STG]   (absent with PRE)
+  uint8_t* planes = stg + (PRE ? 0 : 2 * T6_STG);   // [NPL][3][T6_PLANE]
+  uint8_t* wring = planes + NPL * 3 * T6_PLANE;  // [WS][W_STAGE]
+  constexpr int SR = PRE ? 8 : 16;               // rows of one epilogue warp's transposition tile
+  constexpr int PARTS = 32 / SR, QN = SR / 4;
+  float* scratch_all = reinterpret_cast<float*>(wring + WS * W_STAGE);   // [epilogue warps][SR][36]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + T6_EPI_WARPS * SR * T6_SCR_LD);
   uint64_t* stg_full = bars;             // [2]
   uint64_t* stg_empty = bars + 2;        // [2]
-  uint64_t* pl_full = bars + 4;          // [2]
-  uint64_t* pl_empty = bars + 6;         // [2]
-  uint64_t* acc_full = bars + 8;         // [2]
-  uint64_t* acc_empty = bars + 10;       // [2]
-  uint64_t* w_full = bars + 12;          // [WS]
+  uint64_t* pl_full = bars + 4;          // [NPL <= 4]
+  uint64_t* pl_empty = bars + 8;         // [NPL <= 4]
+  uint64_t* acc_full = bars + 12;        // [2]
+  uint64_t* acc_empty = bars + 14;       // [2]
+  uint64_t* w_full = bars + 16;          // [WS]
   uint64_t* w_empty = w_full + WS;       // [WS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + WS);
   uint32_t* last_flag = tmem_slot + 1;
@@ -220,11 +257,13 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     tma_prefetch_desc(&map_w);
   }
   if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NPL; ++s) {
+      mbar_init(&pl_full[s], PRE ? 1 : T6_CVT_WARPS);
+      mbar_init(&pl_empty[s], 1);
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&stg_full[s], 1);
       mbar_init(&stg_empty[s], T6_CVT_WARPS);
-      mbar_init(&pl_full[s], T6_CVT_WARPS);
-      mbar_init(&pl_empty[s], 1);
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], T6_EPI_WARPS);
     }
@@ -248,6 +287,15 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int mt = tile / p.n_groups;
       const int t0 = (mt % p.t_tiles) * p.t_sub, b0 = (mt / p.t_tiles) * p.b_sub;
       for (int kb = kb0; kb < kb0 + kbn; ++kb, ++kit) {
+        if (PRE) {
+          // three bf16 plane tiles of 128-byte rows straight into operand buffer kit % NPL
+          const int s = kit % NPL;
+          mbar_wait(&pl_empty[s], ((kit / NPL) & 1) ^ 1);
+          mbar_expect_tx(&pl_full[s], (uint32_t)(3 * rows_box * 128));
+          for (int q = 0; q < 3; ++q)
+            tma_load_4d(planes + (s * 3 + q) * T6_PLANE, &map_a, kb * T6_BK, t0, b0, q, &pl_full[s]);
+          continue;
+        }
         const int s = kit & 1;
         mbar_wait(&stg_empty[s], ((kit >> 1) & 1) ^ 1);
         const int kc = kb * T6_BK;
@@ -284,6 +332,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int pa[6] = {0, 1, 2, 0, 1, 0};
     const int pw[6] = {2, 1, 0, 1, 0, 0};
     int kit = 0, wit = 0, li = 0;
+    long long t_grp = clock64() - p.pace;   // issue time of the last MMA group
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
       const int tile = item / S, kbn = min(kb_per, num_kb - (item % S) * kb_per);
       const int pm = min(p.pm, kbn);                       // main accumulators actually written
@@ -294,8 +343,8 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       tc_fence_after();
       const uint32_t acc_base = tmem_base + buf * buf_stride;
       for (int kb = 0; kb < kbn; ++kb, ++kit) {
-        const int s = kit & 1;
-        mbar_wait(&pl_full[s], (kit >> 1) & 1);
+        const int s = kit % NPL;
+        mbar_wait(&pl_full[s], (kit / NPL) & 1);
         tc_fence_after();
         const uint32_t a_base = smem_u32(planes + s * 3 * T6_PLANE);
         for (int j = 0; j < nj; ++j, ++wit) {
@@ -309,6 +358,13 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint64_t dw = make_smem_desc(w_base + pw[t] * (BN * T6_BK * 2));
             const int set = t < 5 ? 0 : 1 + kb % pm;
             const bool first = t < 5 ? (kb == 0 && t == 0) : (kb < pm);
+            // Issue pacing: one group of four MMAs per p.pace cycles, about the time the tensor pipe needs to
+            // execute it, so the queue in front of the pipe does not grow.  Issued as fast as the uniform datapath allows (~10 cycles
+            // per MMA), long bursts of these short MMAs came back with corrupted tiles, non-deterministically
+            // (tools/gemm6_stress.py); paced, the pipe is still never idle.
+            while (clock64() - t_grp < p.pace) {
+            }
+            t_grp = clock64();
 #pragma unroll
             for (int k = 0; k < T6_BK / 16; ++k)
               umma_bf16(acc_base + set * acc_stride + j * BN, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc,
@@ -320,7 +376,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
       umma_commit(&acc_full[buf]);
     }
-  } else if (warp >= 4 && warp < 4 + T6_CVT_WARPS) {
+  } else if (!PRE && warp >= 4 && warp < 4 + T6_CVT_WARPS) {
     // ---------------- converters: staging f32 -> three swizzled bf16 operand tiles ----------------
     const int r = (warp - 4) * 32 + lane;    // tile row
     const int sw = r & 7;
@@ -382,7 +438,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // The two warps of a quadrant take alternate chunks; with a single chunk they split its rows.
     const int ew = warp - (4 + T6_CVT_WARPS);
     const int quad = warp & 3, sib = ew >> 2;     // sibling index 0/1 within the quadrant
-    float* scratch = scratch_all + ew * T6_SCR;
+    float* scratch = scratch_all + ew * SR * T6_SCR_LD;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     int li = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
@@ -402,6 +458,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const uint32_t res_off = p.res ? (uint32_t)p.r_map.off(m) : 0u;
       const uint32_t raw_off = p.out_raw ? (uint32_t)p.o_map.off(m) : 0u;
       const uint32_t act_off = p.out_act ? (uint32_t)p.e_map.off(m) : 0u;
+      const uint32_t pl_off = p.out_pl ? (uint32_t)p.pl_map.off(m) : 0u;
       const uint32_t ok_mask = __ballot_sync(0xffffffffu, row_ok);
       const int buf = li & 1;
       mbar_wait(&acc_full[buf], (li >> 1) & 1);
@@ -416,14 +473,14 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // overlaps the TMEM loads and the transposition instead of following them.
         const int col = n0 + c * 32 + cs * 4;
         const bool col_ok = col < p.N;              // N is a multiple of 32: a chunk is valid as a whole
-        float4 rres[2][4];
+        float4 rres[PARTS][QN];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < PARTS; ++half) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int rr = half * 16 + 4 * q + qrow;
+          for (int q = 0; q < QN; ++q) {
+            const int rr = half * SR + 4 * q + qrow;
             const uint32_t ro = __shfl_sync(0xffffffffu, res_off, rr);
-            const bool want = p.res && col_ok && ((ok_mask >> rr) & 1u) && !(split_rows && half != sib) && S == 1;
+            const bool want = p.res && col_ok && ((ok_mask >> rr) & 1u) && !(split_rows && half / (PARTS / 2) != sib) && S == 1;
             rres[half][q] = want ? __ldg(reinterpret_cast<const float4*>(p.res + ro + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
@@ -438,18 +495,18 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int i = 0; i < 16; ++i) v[h * 16 + i] += u[i];
           }
         }
-        // Transposition through shared memory, 16 rows x 32 columns at a time: the lanes that own the
-        // 16 TMEM rows park them as float4s in a [16][36] scratch tile, then all 32 lanes sweep it four
+        // Transposition through shared memory, SR (16 or 8) rows x 32 columns at a time: the lanes that own the
+        // SR TMEM rows park them as float4s in a [SR][36] scratch tile, then all 32 lanes sweep it four
         // rows per instruction (8 lanes x 16 B = one full 128-byte row segment), so every global access
         // of the epilogue is a float4 in a fully used line.
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), scale4 = make_float4(1.f, 1.f, 1.f, 1.f);
         if (p.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         if (p.scale && col_ok) scale4 = __ldg(reinterpret_cast<const float4*>(p.scale + col));
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (split_rows && half != sib) continue;  // warp-uniform
-          if ((lane >> 4) == half) {
-            float4* dst = reinterpret_cast<float4*>(scratch + (lane & 15) * T6_SCR_LD);
+        for (int half = 0; half < PARTS; ++half) {
+          if (split_rows && half / (PARTS / 2) != sib) continue;  // warp-uniform
+          if (lane / SR == half) {
+            float4* dst = reinterpret_cast<float4*>(scratch + (lane % SR) * T6_SCR_LD);
 #pragma unroll
             for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
@@ -457,8 +514,8 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (S > 1) {
             // split-K: park the raw partial sums of this (tile, split) in the workspace
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int rr = half * 16 + 4 * q + qrow;
+            for (int q = 0; q < QN; ++q) {
+              const int rr = half * SR + 4 * q + qrow;
               *reinterpret_cast<float4*>(ws_mine + (size_t)rr * tile_n + c * 32 + cs * 4) =
                   *reinterpret_cast<const float4*>(scratch + (4 * q + qrow) * T6_SCR_LD + cs * 4);
             }
@@ -466,10 +523,11 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             continue;
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int rr = half * 16 + 4 * q + qrow;
+          for (int q = 0; q < QN; ++q) {
+            const int rr = half * SR + 4 * q + qrow;
             const uint32_t wo = __shfl_sync(0xffffffffu, raw_off, rr);
             const uint32_t ao = __shfl_sync(0xffffffffu, act_off, rr);
+            const uint32_t po = __shfl_sync(0xffffffffu, pl_off, rr);
             if (!(col_ok && ((ok_mask >> rr) & 1u))) continue;
             float4 x = *reinterpret_cast<const float4*>(scratch + (4 * q + qrow) * T6_SCR_LD + cs * 4);
             if (p.bias) {
@@ -483,6 +541,14 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (p.out_act)
               *reinterpret_cast<float4*>(p.out_act + ao + col) =
                   make_float4(elu_ref(x.x), elu_ref(x.y), elu_ref(x.z), elu_ref(x.w));
+            if (p.out_pl) {
+              // the consumer GEMM's A operand, already split into three bf16 planes
+              uint2 h, md, lo;
+              split3_x4(x, h, md, lo);
+              *reinterpret_cast<uint2*>(p.out_pl + po + col) = h;
+              *reinterpret_cast<uint2*>(p.out_pl + p.pl_stride + po + col) = md;
+              *reinterpret_cast<uint2*>(p.out_pl + 2 * p.pl_stride + po + col) = lo;
+            }
           }
           __syncwarp();
         }
@@ -573,22 +639,23 @@ static EncodeTiledFn encode_tiled6() {
   return fn;
 }
 
-template <int BN>
+template <int BN, bool PRE>
 struct T6Cfg {
   static constexpr int W_STAGE = 3 * BN * T6_BK * 2;
-  static constexpr int FIXED = 2 * T6_STG + 2 * 3 * T6_PLANE;             // 160 KB
-  static constexpr int WS_RAW = (209 * 1024 - FIXED) / W_STAGE;
+  // f32 staging (2 x 32 KB) + two operand-plane buffers, or three plane buffers fed directly by TMA
+  static constexpr int FIXED = PRE ? T6_NPL_PRE * 3 * T6_PLANE : 2 * T6_STG + 2 * 3 * T6_PLANE;
+  static constexpr int SCRATCH = T6_EPI_WARPS * (PRE ? 8 : 16) * T6_SCR_LD * 4;
+  static constexpr int WS_RAW = (232448 - 512 - FIXED - SCRATCH) / W_STAGE;
   static constexpr int WS = WS_RAW > 4 ? 4 : WS_RAW;
-  static constexpr int SCRATCH = T6_EPI_WARPS * T6_SCR * 4;
-  static constexpr int SMEM = FIXED + WS * W_STAGE + SCRATCH + (12 + 2 * WS) * 8 + 16;   // barriers + tmem slot + last flag
+  static constexpr int SMEM = FIXED + WS * W_STAGE + SCRATCH + (16 + 2 * WS) * 8 + 16;   // barriers + tmem slot + last flag
   static_assert(SMEM <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static_assert(WS >= 2, "need at least two W stages");
 };
 
-template <int BN>
+template <int BN, bool PRE>
 static void launch6(const Tc6Gemm& g, cudaStream_t st) {
-  using C = T6Cfg<BN>;
-  auto kern = tc6_gemm_kernel<BN, C::WS>;
+  using C = T6Cfg<BN, PRE>;
+  auto kern = tc6_gemm_kernel<BN, C::WS, PRE>;
   static bool attr_set = false;
   if (!attr_set) {
     DSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -600,8 +667,12 @@ static void launch6(const Tc6Gemm& g, cudaStream_t st) {
   p.m_tiles = p.t_tiles * ceil_div(g.B, g.b_sub);
   p.n_groups = ceil_div(g.N, g.nj * BN);
   p.split_k = g.split_k, p.ws = g.ws, p.counters = g.counters;
+  static const int pace64 = [] { const char* e = getenv("DSM_TC6_PACE64"); return e ? atoi(e) : T6_GROUP_CYCLES_64; }();
+  static const int pace32 = [] { const char* e = getenv("DSM_TC6_PACE32"); return e ? atoi(e) : T6_GROUP_CYCLES_32; }();
+  p.pace = BN == 64 ? pace64 : pace32;
   p.bias = g.ep.bias, p.neg = g.ep.neg, p.scale = g.ep.scale, p.res = g.ep.res, p.r_map = g.ep.r_map, p.act = g.ep.act;
   p.out_raw = g.ep.out_raw, p.o_map = g.ep.o_map, p.out_act = g.ep.out_act, p.e_map = g.ep.e_map;
+  p.out_pl = g.ep.out_planes, p.pl_map = g.ep.p_map, p.pl_stride = g.ep.out_plane_stride;
   const long long tiles = (long long)p.m_tiles * p.n_groups * g.split_k;
   static const int max_ctas = [] { const char* e = getenv("DSM_TC6_MAXCTAS"); int v = e ? atoi(e) : 0; return v > 0 ? v : 148; }();
   const int grid = (int)std::min<long long>(tiles, max_ctas);
@@ -613,8 +684,13 @@ bool tc6_supported(const GemmParams& g) {
   if (g.M <= 0 || g.N % 32 != 0 || g.K % 32 != 0 || g.out_bf16) return false;
   if (g.a_map.T <= 0 || g.M % g.a_map.T != 0) return false;
   // TMA: strides in bytes must be multiples of 16
-  if ((g.a_map.stride_t * 4) % 16 != 0 || (g.a_map.stride_b * 4) % 16 != 0) return false;
-  if (reinterpret_cast<uintptr_t>(g.A) % 16 != 0) return false;
+  const int esz = g.a_planes ? 2 : 4;
+  if ((g.a_map.stride_t * esz) % 16 != 0 || (g.a_map.stride_b * esz) % 16 != 0) return false;
+  if (g.a_planes && (g.a_plane_stride * 2) % 16 != 0) return false;
+  if (reinterpret_cast<uintptr_t>(g.a_planes ? (const void*)g.a_planes : g.A) % 16 != 0) return false;
+  if (g.out_planes && (reinterpret_cast<uintptr_t>(g.out_planes) % 8 != 0 || g.p_map.stride_t % 4 != 0 ||
+                       g.p_map.stride_b % 4 != 0 || g.out_plane_stride % 4 != 0))
+    return false;
   // the epilogue reads and writes float4s: every row start must be 16-byte aligned
   auto vec_ok = [](const void* ptr, const RowMap& m) {
     return ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && m.stride_t % 4 == 0 && m.stride_b % 4 == 0);
@@ -673,7 +749,8 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes,
   // (TMEM: two tile buffers of 256 columns, each shared by the correction accumulator and >= 1 main
   // accumulator => at most 128 output columns per tile)
   static const int max_tile_n = [] { const char* e = getenv("DSM_TC6_TILE_N"); int v = e ? atoi(e) : 0; return v >= 32 ? v : 128; }();
-  int nj = std::max(1, std::min(n_sub, std::min(128, max_tile_n) / t.bn));
+  // pre-split A: one column sub-tile per CTA keeps the W ring as deep (in k-blocks) as the operand ring
+  int nj = std::max(1, std::min(n_sub, std::min(g.a_planes ? 64 : 128, max_tile_n) / t.bn));
   while (nj > 1 && m_tiles * ceil_div(n_sub, nj) < 148) nj = (nj + 1) / 2;
   t.nj = nj;
   t.pm = std::max(1, std::min(7, 256 / (nj * t.bn) - 1));
@@ -696,8 +773,20 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes,
     }
     t.split_k = S, t.ws = wsp.ws, t.counters = wsp.counters;
   }
-  // A: f32 [B][T_out][K] window view, box 32 x t_sub x b_sub
-  {
+  t.presplit = g.a_planes != nullptr;
+  if (t.presplit) {
+    // A: bf16 planes [3][B][T_out][K] window view, box 64 x t_sub x b_sub x 1 (128-byte rows, 128B swizzle: the
+    // tile lands in the UMMA operand layout)
+    cuuint64_t gdim[4] = {(cuuint64_t)g.K, (cuuint64_t)t.T_out, (cuuint64_t)t.B, 3};
+    cuuint64_t gstr[3] = {(cuuint64_t)g.a_map.stride_t * 2, (cuuint64_t)g.a_map.stride_b * 2, (cuuint64_t)g.a_plane_stride * 2};
+    if (t.T_out == 1) gstr[0] = gstr[1];
+    cuuint32_t box[4] = {64, (cuuint32_t)t.t_sub, (cuuint32_t)t.b_sub, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode_tiled6()(&t.map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(g.a_planes), gdim,
+                                 gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DSM_CHECK(r == CUDA_SUCCESS, DSM_ERR_CUDA, "tc6 pre-split A tensor map failed (%d): K=%d T=%d B=%d", (int)r, g.K, t.T_out, t.B);
+  } else {
     cuuint64_t gdim[3] = {(cuuint64_t)g.K, (cuuint64_t)t.T_out, (cuuint64_t)t.B};
     cuuint64_t gstr[2] = {(cuuint64_t)g.a_map.stride_t * 4, (cuuint64_t)g.a_map.stride_b * 4};
     if (t.T_out == 1) gstr[0] = gstr[1];      // degenerate time dimension: any legal stride
@@ -732,8 +821,8 @@ Tc6Workspace tc6_make_workspace(Arena& arena) {
 }
 
 void tc6_launch(const Tc6Gemm& t, cudaStream_t st) {
-  if (t.bn == 64) return launch6<64>(t, st);
-  return launch6<32>(t, st);
+  if (t.presplit) return t.bn == 64 ? launch6<64, true>(t, st) : launch6<32, true>(t, st);
+  return t.bn == 64 ? launch6<64, false>(t, st) : launch6<32, false>(t, st);
 }
 
 }  // namespace dsm

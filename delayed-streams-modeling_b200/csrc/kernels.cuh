@@ -44,18 +44,21 @@ void launch_zero_rows(const CommitEntry* entries_dev, int n_entries, int b0, int
 
 // ---- codec transformer (f32) ---------------------------------------------------------------------
 void launch_layernorm(const float* x, RowMap x_map, const float* w, const float* b, float eps, int M, int D,
-                      float* out /*dense [M,D]*/, cudaStream_t st);
+                      float* out /*dense [M,D]*/, cudaStream_t st, __nv_bfloat16* planes = nullptr,
+                      long long plane_stride = 0);   // planes: also the 3-way bf16 split of `out` (see split3_bf16)
 // qkv [M, 3*H*D] (M = B*t) -> q rotated in place; rotated k and v scattered into the rings [B,H,ctx,D].
 void launch_rope_scatter_f32(float* qkv, const RingState& rs, const uint8_t* mask, int B, int t, int H, int D,
                              int context, const float* inv_freq /*[D/2]*/, float* k_ring, float* v_ring, cudaStream_t st);
 // out[m, h*D + d] = softmax(q . K^T * D^-0.5 + mask) . V over the ring, visibility by stored position.
 void launch_codec_attention(const float* qkv, const RingState& rs, const uint8_t* mask, int B, int t, int H, int D,
-                            int context, const float* k_ring, const float* v_ring, float* out, cudaStream_t st);
+                            int context, const float* k_ring, const float* v_ring, float* out, cudaStream_t st,
+                            __nv_bfloat16* planes = nullptr, long long plane_stride = 0);
 
 // ---- RVQ -----------------------------------------------------------------------------------------
 // scores [B, bins] = c2 - x.E^T (from the GEMM); idx = first argmin; residual[b,:] -= E[idx,:]; codes[b*n_q+q] = idx.
 void launch_rvq_select(const float* scores, int B, int bins, const float* embedding /*[bins,qdim]*/, int qdim,
-                       float* residual, long long res_stride, uint32_t* codes, int n_q, int q, cudaStream_t st);
+                       float* residual, long long res_stride, uint32_t* codes, int n_q, int q, cudaStream_t st,
+                       __nv_bfloat16* planes = nullptr, long long plane_stride = 0);
 // decode: out[b, :] = sum_q E_q[codes[b,q], :] over q in [q0, q1)  (quantization.rs:231-248)
 void launch_rvq_gather_sum(const uint32_t* codes, int n_q, int q0, int q1, const float* embeddings /*[n_q][bins][qdim]*/,
                            int bins, int qdim, int B, float* out, cudaStream_t st);

@@ -36,9 +36,21 @@ bool codec_gemm_tc_enabled() {
   return !(e && std::string(e) == "simt");
 }
 
-std::shared_ptr<CodecGemm> make_codec_gemm(Arena& arena, const GemmParams& g, const std::vector<float>& w_host,
+// Skinny codec GEMMs (transformer, RVQ scores) take their A operand pre-split into bf16 planes written by the
+// producing kernel; DSM_CODEC_PRESPLIT=0 keeps the f32 A path (converter warps) for A/B runs.
+bool codec_presplit_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DSM_CODEC_PRESPLIT");
+    return codec_gemm_tc_enabled() && !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+std::shared_ptr<CodecGemm> make_codec_gemm(Arena& arena, const GemmParams& g_in, const std::vector<float>& w_host,
                                            const Tc6Workspace& wsp) {
   auto c = std::make_shared<CodecGemm>();
+  GemmParams g = g_in;
+  if (!(codec_gemm_tc_enabled() && tc6_supported(g))) g.a_planes = nullptr, g.out_planes = nullptr;
   c->g = g;
   DSM_CHECK(w_host.size() == (size_t)g.N * g.K, DSM_ERR_SHAPE, "codec gemm: weight has %zu elements, expected %d x %d",
             w_host.size(), g.N, g.K);
@@ -76,6 +88,11 @@ void CodecTransformer::init(Arena& arena, const dsm_mimi_spec& s, int batch, con
   qkv = arena.alloc<float>(M * 3 * D);
   attn = arena.alloc<float>(M * D);
   hbuf = arena.alloc<float>(M * ff);
+  if (codec_presplit_enabled()) {
+    xn_pl = arena.alloc<__nv_bfloat16>(3 * M * D);
+    attn_pl = arena.alloc<__nv_bfloat16>(3 * M * D);
+    h_pl = arena.alloc<__nv_bfloat16>(3 * M * ff);
+  }
   const float sd = 1.f / sqrtf((float)D), sff = 1.f / sqrtf((float)ff);
   layers.resize(L);
   for (int l = 0; l < L; ++l) {
@@ -108,18 +125,24 @@ void CodecTransformer::append_plan(Plan& plan, float* x, RowMap x_map, const uin
     GemmParams g;     // qkv = in_proj(norm1(x))
     g.A = xn, g.a_map = dense_rows(1, D), g.M = M, g.N = 3 * D, g.K = D;
     g.out_raw = qkv, g.o_map = dense_rows(1, 3 * D);
+    const long long MD = (long long)M * D, MF = (long long)M * ff;
+    if (xn_pl) g.a_planes = xn_pl, g.a_plane_stride = MD;
     auto g_qkv = make_codec_gemm(*arena_, g, yl.h_in_proj, wsp);
     GemmParams o;     // x <- x + layer_scale_1 * out_proj(attn)     (batched_transformer.rs:347-349)
     o.A = attn, o.a_map = dense_rows(1, D), o.M = M, o.N = D, o.K = D;
     o.scale = yl.ls1, o.res = x, o.r_map = x_map, o.out_raw = x, o.o_map = x_map;
+    if (attn_pl) o.a_planes = attn_pl, o.a_plane_stride = MD;
     auto g_out = make_codec_gemm(*arena_, o, yl.h_out_proj, wsp);
     GemmParams f1;    // h = gelu(linear1(norm2(x)))
     f1.A = xn, f1.a_map = dense_rows(1, D), f1.M = M, f1.N = ff, f1.K = D;
     f1.act = 1, f1.out_raw = hbuf, f1.o_map = dense_rows(1, ff);
+    if (xn_pl) f1.a_planes = xn_pl, f1.a_plane_stride = MD;
+    if (h_pl) f1.out_planes = h_pl, f1.p_map = dense_rows(1, ff), f1.out_plane_stride = MF;
     auto g_f1 = make_codec_gemm(*arena_, f1, yl.h_lin1, wsp);
     GemmParams f2;    // x <- x + layer_scale_2 * linear2(h)   (:360-361)
     f2.A = hbuf, f2.a_map = dense_rows(1, ff), f2.M = M, f2.N = D, f2.K = ff;
     f2.scale = yl.ls2, f2.res = x, f2.r_map = x_map, f2.out_raw = x, f2.o_map = x_map;
+    if (h_pl && g_f1->use_tc) f2.a_planes = h_pl, f2.a_plane_stride = MF;   // planes exist only if linear1 wrote them
     auto g_f2 = make_codec_gemm(*arena_, f2, yl.h_lin2, wsp);
     yl.h_in_proj = std::vector<float>();
     yl.h_out_proj = std::vector<float>();
@@ -127,14 +150,14 @@ void CodecTransformer::append_plan(Plan& plan, float* x, RowMap x_map, const uin
     yl.h_lin2 = std::vector<float>();
     const Layer y = yl;
     plan.push_back([=](cudaStream_t st) {
-      launch_layernorm(x, x_map, y.ln1w, y.ln1b, self->eps, M, self->D, self->xn, st);
+      launch_layernorm(x, x_map, y.ln1w, y.ln1b, self->eps, M, self->D, self->xn, st, self->xn_pl, MD);
       run_codec_gemm(*g_qkv, st);
       launch_rope_scatter_f32(self->qkv, self->ring, d_mask, self->B, self->T, self->H, self->hd, self->ctx,
                               self->inv_freq, y.k_ring, y.v_ring, st);
       launch_codec_attention(self->qkv, self->ring, d_mask, self->B, self->T, self->H, self->hd, self->ctx, y.k_ring,
-                             y.v_ring, self->attn, st);
+                             y.v_ring, self->attn, st, self->attn_pl, MD);
       run_codec_gemm(*g_out, st);
-      launch_layernorm(x, x_map, y.ln2w, y.ln2b, self->eps, M, self->D, self->xn, st);
+      launch_layernorm(x, x_map, y.ln2w, y.ln2b, self->eps, M, self->D, self->xn, st, self->xn_pl, MD);
       run_codec_gemm(*g_f1, st);
       run_codec_gemm(*g_f2, st);
     });
@@ -510,7 +533,12 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
     GemmParams gp;
     gp.A = latent, gp.a_map = dense_rows(1, D), gp.M = Bc, gp.N = 2 * qd, gp.K = D;
     gp.out_raw = resid, gp.o_map = dense_rows(1, 2 * qd);
+    // the residual also as bf16 planes (same [B, 2*qd] row layout): the 32 score GEMMs read it pre-split
+    const long long RP = (long long)Bc * 2 * qd;
+    __nv_bfloat16* resid_pl = codec_presplit_enabled() ? arena.alloc<__nv_bfloat16>((size_t)3 * RP) : nullptr;
+    if (resid_pl) gp.out_planes = resid_pl, gp.p_map = dense_rows(1, 2 * qd), gp.out_plane_stride = RP;
     auto g_proj = make_codec_gemm(arena, gp, wf, wsp);
+    if (!g_proj->use_tc) resid_pl = nullptr;     // the CUDA-core GEMM does not write planes
     // codebook embeddings on the host once more for the score GEMMs' weight planes
     std::vector<float> emb_host((size_t)nq * bins * qd);
     DSM_CUDA(cudaMemcpy(emb_host.data(), emb_all, emb_host.size() * sizeof(float), cudaMemcpyDeviceToHost));
@@ -521,6 +549,7 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
       s.M = Bc, s.N = bins, s.K = qd;
       s.bias = c2_all + (size_t)q * bins, s.neg = 1;     // c2 - x.e   (quantization.rs:128-129)
       s.out_raw = scores, s.o_map = dense_rows(1, bins);
+      if (resid_pl) s.a_planes = resid_pl + (q == 0 ? 0 : qd), s.a_plane_stride = RP;
       std::vector<float> Eq(emb_host.begin() + (size_t)q * bins * qd, emb_host.begin() + (size_t)(q + 1) * bins * qd);
       g_score[q] = make_codec_gemm(arena, s, Eq, wsp);
     }
@@ -532,7 +561,8 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
       run_codec_gemm(*g_proj, st);
       for (int q = 0; q < nq; ++q) {
         run_codec_gemm(*g_score[q], st);
-        launch_rvq_select(sc, Bc, bins, emb + (size_t)q * bins * qd, qd, res + (q == 0 ? 0 : qd), 2 * qd, codes, nq, q, st);
+        launch_rvq_select(sc, Bc, bins, emb + (size_t)q * bins * qd, qd, res + (q == 0 ? 0 : qd), 2 * qd, codes, nq, q, st,
+                          resid_pl ? resid_pl + (q == 0 ? 0 : qd) : nullptr, RP);
       }
     });
   }

@@ -20,6 +20,7 @@ struct CodecGemm {
   bool use_tc = false;
 };
 bool codec_gemm_tc_enabled();
+bool codec_presplit_enabled();
 std::shared_ptr<CodecGemm> make_codec_gemm(Arena& arena, const GemmParams& g, const std::vector<float>& w_host,
                                            const Tc6Workspace& wsp = Tc6Workspace());
 void run_codec_gemm(const CodecGemm& c, cudaStream_t st);
@@ -32,6 +33,8 @@ struct CodecTransformer {
   RingState ring{};
   float* inv_freq = nullptr;
   float *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr;
+  // the same activations as three bf16 planes ([3][rows][cols]) for the pre-split GEMM path (null when off)
+  __nv_bfloat16 *xn_pl = nullptr, *attn_pl = nullptr, *h_pl = nullptr;
   struct Layer {
     float *ln1w, *ln1b, *ln2w, *ln2b, *ls1, *ls2;
     float *k_ring, *v_ring;

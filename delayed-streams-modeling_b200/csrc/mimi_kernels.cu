@@ -205,7 +205,8 @@ void launch_zero_rows(const CommitEntry* entries_dev, int n_entries, int b0, int
 template <int D>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, RowMap x_map,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
-                                                         float eps, int M, float* __restrict__ out) {
+                                                         float eps, int M, float* __restrict__ out,
+                                                         __nv_bfloat16* __restrict__ planes, long long plane_stride) {
   constexpr int V = D / 128;  // float4 per lane
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int m = blockIdx.x * (blockDim.x / 32) + warp;
@@ -238,13 +239,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     o.z = (v[i].z - mean) * rstd * g.z + bb.z;
     o.w = (v[i].w - mean) * rstd * g.w + bb.w;
     *reinterpret_cast<float4*>(orow + c) = o;
+    if (planes) store_planes4(planes, plane_stride, (long long)m * D + c, o);
   }
 }
 
 void launch_layernorm(const float* x, RowMap x_map, const float* w, const float* b, float eps, int M, int D,
-                      float* out, cudaStream_t st) {
+                      float* out, cudaStream_t st, __nv_bfloat16* planes, long long plane_stride) {
   DSM_CHECK(D == 512, DSM_ERR_UNSUPPORTED, "layernorm: D=%d (only 512)", D);
-  layernorm_kernel<512><<<ceil_div(M, 8), 256, 0, st>>>(x, x_map, w, b, eps, M, out);
+  layernorm_kernel<512><<<ceil_div(M, 8), 256, 0, st>>>(x, x_map, w, b, eps, M, out, planes, plane_stride);
   check_launch("layernorm");
 }
 
@@ -298,7 +300,8 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
                                                                const uint8_t* __restrict__ mask, int t, int H,
                                                                int context, const float* __restrict__ k_ring,
                                                                const float* __restrict__ v_ring,
-                                                               float* __restrict__ out) {
+                                                               float* __restrict__ out,
+                                                               __nv_bfloat16* __restrict__ planes, long long plane_stride) {
   static_assert(D == 64, "lane layout assumes 16 lanes x float4 per key");
   extern __shared__ float sm[];
   float* sc = sm;                       // [TQ][context]
@@ -434,15 +437,25 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
     float v = 0.f;
 #pragma unroll
     for (int gg = 0; gg < 8; ++gg) v += red[(gg * TQ + s) * D + d];
-    out[(long long)(b * t + s) * HD + h * D + d] = v;
+    const long long o = (long long)(b * t + s) * HD + h * D + d;
+    out[o] = v;
+    if (planes) {
+      uint16_t ph, pm, pl;
+      split3_bf16(v, ph, pm, pl);
+      reinterpret_cast<uint16_t*>(planes)[o] = ph;
+      reinterpret_cast<uint16_t*>(planes)[plane_stride + o] = pm;
+      reinterpret_cast<uint16_t*>(planes)[2 * plane_stride + o] = pl;
+    }
   }
 }
 
 void launch_codec_attention(const float* qkv, const RingState& rs, const uint8_t* mask, int B, int t, int H, int D,
-                            int context, const float* k_ring, const float* v_ring, float* out, cudaStream_t st) {
+                            int context, const float* k_ring, const float* v_ring, float* out, cudaStream_t st,
+                            __nv_bfloat16* planes, long long plane_stride) {
   DSM_CHECK(D == 64 && t <= 2, DSM_ERR_UNSUPPORTED, "codec_attention: D=%d t=%d", D, t);
   size_t smem = (size_t)(2 * context + 8 * 2 * D) * sizeof(float);
-  codec_attention_kernel<64, 2><<<B * H, 128, smem, st>>>(qkv, rs, mask, t, H, context, k_ring, v_ring, out);
+  codec_attention_kernel<64, 2><<<B * H, 128, smem, st>>>(qkv, rs, mask, t, H, context, k_ring, v_ring, out, planes,
+                                                          plane_stride);
   check_launch("codec_attention");
 }
 
@@ -453,7 +466,8 @@ void launch_codec_attention(const float* qkv, const RingState& rs, const uint8_t
 __global__ void __launch_bounds__(256) rvq_select_kernel(const float* __restrict__ scores, int bins,
                                                           const float* __restrict__ embedding, int qdim,
                                                           float* __restrict__ residual, long long res_stride,
-                                                          uint32_t* __restrict__ codes, int n_q, int q) {
+                                                          uint32_t* __restrict__ codes, int n_q, int q,
+                                                          __nv_bfloat16* __restrict__ planes, long long plane_stride) {
   __shared__ float s_val[8];
   __shared__ int s_idx[8];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -483,12 +497,26 @@ __global__ void __launch_bounds__(256) rvq_select_kernel(const float* __restrict
   if (tid == 0) codes[(long long)b * n_q + q] = (uint32_t)bi;
   const float* e = embedding + (long long)bi * qdim;
   float* r = residual + (long long)b * res_stride;
-  for (int d = tid; d < qdim; d += blockDim.x) r[d] -= e[d];
+  for (int d = tid; d < qdim; d += blockDim.x) {
+    const float v = r[d] - e[d];
+    r[d] = v;
+    if (planes) {
+      // the next codebook's score GEMM reads the residual as three bf16 planes (same row layout as `residual`)
+      const long long o = (long long)b * res_stride + d;
+      uint16_t ph, pm, pl;
+      split3_bf16(v, ph, pm, pl);
+      reinterpret_cast<uint16_t*>(planes)[o] = ph;
+      reinterpret_cast<uint16_t*>(planes)[plane_stride + o] = pm;
+      reinterpret_cast<uint16_t*>(planes)[2 * plane_stride + o] = pl;
+    }
+  }
 }
 
 void launch_rvq_select(const float* scores, int B, int bins, const float* embedding, int qdim, float* residual,
-                       long long res_stride, uint32_t* codes, int n_q, int q, cudaStream_t st) {
-  rvq_select_kernel<<<B, 256, 0, st>>>(scores, bins, embedding, qdim, residual, res_stride, codes, n_q, q);
+                       long long res_stride, uint32_t* codes, int n_q, int q, cudaStream_t st, __nv_bfloat16* planes,
+                       long long plane_stride) {
+  rvq_select_kernel<<<B, 256, 0, st>>>(scores, bins, embedding, qdim, residual, res_stride, codes, n_q, q, planes,
+                                       plane_stride);
   check_launch("rvq_select");
 }
 

@@ -24,7 +24,7 @@ for (B, T, C, k, s, N) in cases:
     flat = buf.reshape(B, -1).astype(np.float64)
     for t in range(T):
         ref[:, t] = flat[:, t * s * C: t * s * C + k * C] @ W.astype(np.float64).T + bias
-    for impl in (0, 1):
+    for impl in (0, 1, 2, 3):
         out = np.zeros((B * T, N), np.float32)
         check(lib.dsm_debug_gemm_f32(impl, B, T, (S + T_in) * C, s * C, N, k * C, ptr(buf), buf.size, ptr(W), ptr(bias), ptr(out)))
         err = np.abs(out.reshape(B, T, N) - ref).max() / np.abs(ref).max()

@@ -9,6 +9,7 @@ from dsm_b200._lib import check, ptr
 lib = _lib.load()
 rng = np.random.default_rng(0)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+impl = int(sys.argv[2]) if len(sys.argv) > 2 else 1     # 1: f32 A through the converter warps, 2: pre-split A planes
 # (B, T_out, C_in, k, stride, C_out)
 cases = [(2, 2, 1024, 2, 1, 4096), (2, 16, 512, 2, 1, 1536), (2, 96, 256, 2, 1, 640), (2, 480, 128, 2, 1, 256),
          (2, 1920, 64, 3, 1, 32), (2, 1920, 32, 1, 1, 64), (3, 2, 512, 7, 1, 1024), (2, 2, 512, 1, 1, 2048),
@@ -28,7 +29,7 @@ for (B, T, C, k, s, N) in cases:
     worst = 0.0
     for r in range(reps):
         out = np.zeros((B * T, N), np.float32)
-        check(lib.dsm_debug_gemm_f32(1, B, T, (S + T_in) * C, s * C, N, k * C, ptr(buf), buf.size, ptr(W), ptr(bias), ptr(out)))
+        check(lib.dsm_debug_gemm_f32(impl, B, T, (S + T_in) * C, s * C, N, k * C, ptr(buf), buf.size, ptr(W), ptr(bias), ptr(out)))
         if first is None:
             first = out
         elif not np.array_equal(first, out):
