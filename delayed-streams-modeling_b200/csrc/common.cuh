@@ -85,7 +85,8 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU(alpha = 1) as the reference computes it: exp(x) - 1 for x <= 0 (candle Activation::Elu), not expm1
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expf(x) - 1.f; }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
 

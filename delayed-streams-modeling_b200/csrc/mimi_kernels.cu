@@ -35,6 +35,7 @@ void launch_ring_advance(const RingState& rs, const uint8_t* mask, int B, int t,
 // ([B, T, C] f32 written twice: raw for the residual path, ELU'd for the next conv).
 // One thread produces 4 consecutive channels of one time step -> float4 coalesced stores.
 // ================================================================================================
+constexpr int IC_R = 16;   // time steps per thread: 256-step tiles amortise the weight staging of a CTA
 template <int KMAX>
 __global__ void __launch_bounds__(256) init_conv_kernel(const float* __restrict__ pcm, const float* __restrict__ state,
                                                          int S, const float* __restrict__ w,
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(256) init_conv_kernel(const float* __restrict_
   float* sx = sm + C * k;         // [tile_t + k - 1]
   const int b = blockIdx.y;
   const int c4n = C / 4;
-  const int tile_t = blockDim.x / c4n * 4;   // each thread handles 4 time steps
+  const int tile_t = blockDim.x / c4n * IC_R;   // each thread handles IC_R time steps
   const int t0 = blockIdx.x * tile_t;
   for (int i = threadIdx.x; i < C * k; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < tile_t + k - 1; i += blockDim.x) {
@@ -67,9 +68,9 @@ __global__ void __launch_bounds__(256) init_conv_kernel(const float* __restrict_
 #pragma unroll
     for (int q = 0; q < KMAX; ++q) wreg[j][q] = q < k ? sw[(c4 * 4 + j) * k + q] : 0.f;
   }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int tl = tt + r * (tile_t / 4);
+#pragma unroll 4
+  for (int r = 0; r < IC_R; ++r) {
+    const int tl = tt + r * (tile_t / IC_R);
     const int t = t0 + tl;
     if (t >= T) continue;
     float acc[4] = {breg[0], breg[1], breg[2], breg[3]};
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(256) init_conv_kernel(const float* __restrict_
 void launch_init_conv(const float* pcm, const float* state, int S, const float* w, const float* bias, int B, int T,
                       int C, int k, float* out_raw, RowMap raw_map, float* out_act, RowMap act_map, cudaStream_t st) {
   DSM_CHECK(k <= 8 && C % 4 == 0 && 256 % (C / 4) == 0, DSM_ERR_UNSUPPORTED, "init_conv: k=%d C=%d unsupported", k, C);
-  const int tile_t = 256 / (C / 4) * 4;
+  const int tile_t = 256 / (C / 4) * IC_R;
   dim3 grid(ceil_div(T, tile_t), B);
   size_t smem = (size_t)(C * k + tile_t + k - 1) * sizeof(float);
   init_conv_kernel<8><<<grid, 256, smem, st>>>(pcm, state, S, w, bias, T, C, k, out_raw, raw_map, out_act, act_map);
