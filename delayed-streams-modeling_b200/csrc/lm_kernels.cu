@@ -162,8 +162,10 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p, uint64_t pol) {
   return r;
 }
 
-template <int D, int UNROLL, bool EVICT>
-__global__ void __launch_bounds__(128, 8) lm_attention_kernel(const __nv_bfloat16* __restrict__ q, RingState rs,
+// GROUPS independent 128-thread groups per CTA, each walking its own (stream, head) items (named barriers), so
+// that a persistent one-CTA-per-SM grid still overlaps the phases of two items.
+template <int D, int UNROLL, bool EVICT, int GROUPS>
+__global__ void __launch_bounds__(128 * GROUPS, GROUPS == 1 ? 8 : 3) lm_attention_kernel(const __nv_bfloat16* __restrict__ q, RingState rs,
                                                             const uint8_t* __restrict__ mask, int H, int context,
                                                             int n_items, const __nv_bfloat16* __restrict__ k_ring,
                                                             const __nv_bfloat16* __restrict__ v_ring,
@@ -172,21 +174,25 @@ __global__ void __launch_bounds__(128, 8) lm_attention_kernel(const __nv_bfloat1
   constexpr int KPW = 32 / LPK;       // keys per warp-load
   constexpr int NW = 4;
   extern __shared__ float sm[];
-  float* sc = sm;                     // [context] scores, then reused as [NW][D] partial outputs
-  float* red = sm;
-  __shared__ float s_red[NW];
-  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int grp = threadIdx.x / 128;
+  const int gsz = context > 4 * D ? context : 4 * D;   // floats of one group's buffer
+  float* sc = sm + grp * gsz;         // [context] scores, then reused as [NW][D] partial outputs
+  float* red = sc;
+  __shared__ float s_red_all[GROUPS][NW];
+  float* s_red = s_red_all[grp];
+  const int tid = threadIdx.x % 128, warp = tid / 32, lane = tid % 32;
+  auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
   const int HD = H * D;
   const uint64_t pol = EVICT ? l2_evict_first_policy() : 0;
   // grid == n_items: one (stream, head) per CTA.  A smaller grid walks the items (persistent form: every
   // CTA is resident at once, so a co-scheduled kernel with large CTAs is never starved of SM space).
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  for (int item = blockIdx.x * GROUPS + grp; item < n_items; item += gridDim.x * GROUPS) {
   const int b = item / H, h = item % H;
   __nv_bfloat16* orow = out + (long long)b * HD + h * D;
   const bool active = mask ? mask[b] != 0 : true;
   if (!active) {
     // an inactive stream's output is never consumed (asr.rs:221-223); skip the ring read
-    for (int d = tid; d < D; d += blockDim.x) orow[d] = __float2bfloat16_rn(0.f);
+    for (int d = tid; d < D; d += 128) orow[d] = __float2bfloat16_rn(0.f);
     continue;
   }
   const uint32_t p0 = rs.cur_pos[b];
@@ -227,25 +233,25 @@ __global__ void __launch_bounds__(128, 8) lm_attention_kernel(const __nv_bfloat1
       if (c8 == 0 && j < n) sc[j] = s;
     }
   }
-  __syncthreads();
+  group_sync();
 
   // ---- softmax (f32) ----
   float mx = -INFINITY;
-  for (int j = tid; j < n; j += blockDim.x) mx = fmaxf(mx, sc[j]);
+  for (int j = tid; j < n; j += 128) mx = fmaxf(mx, sc[j]);
   mx = warp_max(mx);
   if (lane == 0) s_red[warp] = mx;
-  __syncthreads();
+  group_sync();
   mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-  __syncthreads();
+  group_sync();
   float sum = 0.f;
-  for (int j = tid; j < n; j += blockDim.x) {
+  for (int j = tid; j < n; j += 128) {
     const float e = __expf(sc[j] - mx);
     sc[j] = e;
     sum += e;
   }
   sum = warp_sum(sum);
   if (lane == 0) s_red[warp] = sum;
-  __syncthreads();
+  group_sync();
   const float inv = 1.f / (s_red[0] + s_red[1] + s_red[2] + s_red[3]);
 
   // ---- P.V ----
@@ -280,17 +286,17 @@ __global__ void __launch_bounds__(128, 8) lm_attention_kernel(const __nv_bfloat1
 #pragma unroll
     for (int o = LPK; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
   }
-  __syncthreads();                    // every warp is done reading the probabilities in sc[]
+  group_sync();                    // every warp is done reading the probabilities in sc[]
   if (sub == 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[warp * D + c8 * 8 + i] = acc[i];
   }
-  __syncthreads();
-  for (int d = tid; d < D; d += blockDim.x) {
+  group_sync();
+  for (int d = tid; d < D; d += 128) {
     const float v = (red[d] + red[D + d] + red[2 * D + d] + red[3 * D + d]) * inv;
     orow[d] = __float2bfloat16_rn(v);
   }
-  __syncthreads();                    // red[] is the next item's score buffer
+  group_sync();                    // red[] is the next item's score buffer
   }
 }
 
@@ -304,25 +310,31 @@ void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint
   if (!carveout_set) {
     const char* e = getenv("DSM_ATTN_CARVEOUT");
     if (e && e[0] == '1') {
-      DSM_CUDA(cudaFuncSetAttribute(lm_attention_kernel<128, 8, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+      DSM_CUDA(cudaFuncSetAttribute(lm_attention_kernel<128, 8, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
-      DSM_CUDA(cudaFuncSetAttribute(lm_attention_kernel<64, 8, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+      DSM_CUDA(cudaFuncSetAttribute(lm_attention_kernel<64, 8, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
     }
     carveout_set = true;
   }
   static const int max_ctas = [] { const char* e = getenv("DSM_ATTN_CTAS"); return e ? atoi(e) : 0; }();
   static const int evict = [] { const char* e = getenv("DSM_ATTN_EVICT_FIRST"); return e ? atoi(e) : 0; }();
+  // DSM_ATTN_FAT=n: persistent grid of n CTAs of 2 x 128 threads with 12 loads in flight per thread (experiment:
+  // a footprint that leaves most of an SM to a co-resident codec GEMM CTA)
+  static const int fat = [] { const char* e = getenv("DSM_ATTN_FAT"); return e ? atoi(e) : 0; }();
   const int items = B * H;
   const int grid = max_ctas > 0 ? std::min(items, max_ctas) : items;
-  if (D == 128 && evict)
-    lm_attention_kernel<128, 8, true><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
+  if (fat > 0 && D == 128) {
+    lm_attention_kernel<128, 12, false, 2><<<std::min(fat, (items + 1) / 2), 256, 2 * smem, st>>>(q, rs, mask, H, context, items, k_ring,
+                                                                                                 v_ring, out);
+  } else if (D == 128 && evict)
+    lm_attention_kernel<128, 8, true, 1><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
   else if (D == 128)
-    lm_attention_kernel<128, 8, false><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
+    lm_attention_kernel<128, 8, false, 1><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
   else if (D == 64 && evict)
-    lm_attention_kernel<64, 8, true><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
+    lm_attention_kernel<64, 8, true, 1><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
   else if (D == 64)
-    lm_attention_kernel<64, 8, false><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
+    lm_attention_kernel<64, 8, false, 1><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
   else
     fail(DSM_ERR_UNSUPPORTED, "lm_attention: head_dim %d (64 or 128)", D);
   check_launch("lm_attention");
