@@ -331,8 +331,8 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
   // reduced together: at each butterfly step a lane keeps half of its values and hands the other half to its
   // partner (8 shuffles per iteration instead of 32; the pairing order 8,4,2,1 and therefore the rounding are
   // those of a plain xor-shuffle tree).  The visibility mask is applied later, once per score.
-  constexpr int UNR = 4;
-  static_assert(TQ == 2 && UNR == 4, "the multi-value reduction below is written for 8 values per lane");
+  constexpr int UNR = 8;     // keys in flight per lane group: 8 x 16 B per lane, ~115 KB per SM at 7 CTAs
+  static_assert(TQ == 2 && UNR % 4 == 0, "the multi-value reduction below takes 4 keys x 2 queries at a time");
   const bool h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
   const int my_u = (h8 ? 2 : 0) + (h4 ? 1 : 0), my_s = h2 ? 1 : 0;   // the (key, query) this lane ends up with
   for (int j0 = warp * 2 * UNR; j0 < context; j0 += 8 * UNR) {
@@ -343,12 +343,14 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
       kv[u] = j < context ? __ldg(reinterpret_cast<const float4*>(kb + (long long)j * D + c4 * 4))
                           : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+#pragma unroll
+    for (int ub = 0; ub < UNR; ub += 4) {
     float v8[8];   // index u * 2 + s
 #pragma unroll
-    for (int u = 0; u < UNR; ++u)
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int s = 0; s < TQ; ++s)
-        v8[u * 2 + s] = q[s].x * kv[u].x + q[s].y * kv[u].y + q[s].z * kv[u].z + q[s].w * kv[u].w;
+        v8[u * 2 + s] = q[s].x * kv[ub + u].x + q[s].y * kv[ub + u].y + q[s].z * kv[ub + u].z + q[s].w * kv[ub + u].w;
     float v4[4], v2[2];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -362,8 +364,9 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
     }
     float v1 = (h2 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? v2[0] : v2[1], 2);
     v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-    const int j = j0 + 2 * my_u + sub;
+    const int j = j0 + 2 * (ub + my_u) + sub;
     if ((lane & 1) == 0 && j < context && my_s < t) sc[my_s * context + j] = v1 * scale;
+    }
   }
   __syncthreads();
 
