@@ -61,3 +61,47 @@ def test_repeated_launches_are_bit_identical(impl):
         for _ in range(5):
             again = _run(lib, impl, B, T, N, k * C, buf, W, bias, sb, st)
             assert np.array_equal(first, again), f"{shape}: results differ between launches"
+
+
+# ---- the LM's bf16 tcgen05 GEMM (gemm_tc) ---------------------------------------------------------
+LM_SHAPES = [(256, 6144, 2048, 0), (256, 8000, 2048, 0), (256, 11264, 2048, 2), (3, 768, 256, 0), (64, 128, 64, 0),
+             (100, 256, 256, 0), (130, 512, 192, 2), (1, 6144, 2048, 0)]
+
+
+def test_lm_gemm_accuracy_and_repeated_launches():
+    """Values against float64 on the bf16-rounded operands (f32 accumulation: rel 2e-5; bf16 gate output: 1e-2);
+    repeated launches agree to rounding (split-K partial sums meet through f32 atomics, so the order of the
+    additions, not more, may differ) -- the corruption this guards against was 1e-2 of the value range."""
+    from dsm_b200 import _lib
+    from dsm_b200._lib import check, ptr
+    from dsm_b200.weights import round_bf16, to_bf16_bits
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    for (M, N, K, mode) in LM_SHAPES:
+        X = rng.standard_normal((M, K), dtype=np.float32)
+        W = rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)
+        ref = round_bf16(X).astype(np.float64) @ round_bf16(W).astype(np.float64).T
+        Xb, Wb = to_bf16_bits(X), to_bf16_bits(W)          # keep alive across the C calls
+        first = None
+        for _ in range(4):
+            out = np.zeros((M, N), np.float32)
+            gate = np.zeros((M, N // 2), np.uint16)
+            check(lib.dsm_debug_gemm_bf16(1, mode, M, N, K, ptr(Xb), ptr(Wb), ptr(out), ptr(gate)))
+            got = gate.copy() if mode == 2 else out
+            if first is None:
+                first = got
+                if mode == 2:
+                    h = N // 2
+                    r = ref[:, :h] / (1 + np.exp(-ref[:, :h])) * ref[:, h:]
+                    val = (gate.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+                    assert np.abs(val - r).max() / np.abs(r).max() < 1e-2, (M, N, K)
+                else:
+                    assert np.abs(out - ref).max() / np.abs(ref).max() < 2e-5, (M, N, K)
+            else:
+                if mode == 2:
+                    a = (first.astype(np.uint32) << 16).view(np.float32)
+                    b = (got.astype(np.uint32) << 16).view(np.float32)
+                    tol = 1e-2          # one bf16 ulp of the output
+                else:
+                    a, b, tol = first, got, 1e-6
+                assert np.abs(a - b).max() <= tol * np.abs(a).max(), f"{(M, N, K, mode)}: results differ between launches"
