@@ -201,19 +201,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   } else if (warp == 1 && elect_one()) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc = make_idesc(BMX);
-    // Issue pacing, as in gemm_tc6.cu: a stage's MMAs are not issued before the tensor pipe has had the time to
-    // execute the previous stage's (M = 128: N / 2 cycles per MMA), so the queue in front of the pipe cannot
-    // grow.  These GEMMs are fed by TMA at HBM rate, so the pause is normally already over when a stage lands.
-    constexpr long long PACE = (long long)NACC * (TC_BK / TC_UK) * (BMX / 2);
-    long long t_grp = clock64() - PACE;
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
-      while (clock64() - t_grp < PACE) {
-      }
-      t_grp = clock64();
       const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
       const uint32_t b_addr = a_addr + NACC * A_BYTES;
       const uint64_t db = make_smem_desc(b_addr);

@@ -175,9 +175,15 @@ constexpr int T6_PLANE = T6_BM * T6_BK * 2;      // 16 KB per bf16 plane tile
 constexpr int T6_EPI_WARPS = 8;      // two per TMEM lane quadrant
 constexpr int T6_CVT_WARPS = 4;      // one converter thread per tile row
 constexpr int T6_THREADS = (4 + T6_CVT_WARPS + T6_EPI_WARPS) * 32;
-// Minimum spacing of the 4-MMA issue groups (see the MMA issuer), overridable for A/B runs (DSM_TC6_PACE64/32)
-constexpr int T6_GROUP_CYCLES_64 = 128, T6_GROUP_CYCLES_32 = 176;
+// Optional minimum spacing of the 4-MMA issue groups in cycles (DSM_TC6_PACE64/32; 0 = off, the default).  It was
+// the first, wrong, explanation of the corrupted tiles that the proxy fence in the converter warps cured; kept as
+// an A/B switch.
 constexpr int T6_NPL_PRE = 3;        // operand-plane buffers of the pre-split variant (48 KB each)
+#ifndef T6_NPL_F32
+#define T6_NPL_F32 2
+#endif
+// Operand-plane buffers of the f32-A variant.  Measured: two buffers + two W stages beat one buffer + four W
+// stages (codec step 3.01 vs 3.17 ms), so the converter/MMA overlap is worth more than the deeper W ring.
 constexpr int T6_SCR_LD = 36;        // floats per scratch row: 32 columns + 4 (float4 rows stay conflict-free)
 
 }  // namespace
@@ -223,7 +229,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzle atoms need a 1024-byte aligned base
-  constexpr int NPL = PRE ? T6_NPL_PRE : 2;      // operand-plane buffers
+  constexpr int NPL = PRE ? T6_NPL_PRE : T6_NPL_F32;      // operand-plane buffers
   uint8_t* stg = smem;                           // [2][T6_STG]   (absent with PRE)
   uint8_t* planes = stg + (PRE ? 0 : 2 * T6_STG);   // [NPL][3][T6_PLANE]
   uint8_t* wring = planes + NPL * 3 * T6_PLANE;  // [WS][W_STAGE]
@@ -351,6 +357,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const int ws = wit % WS;
           mbar_wait(&w_full[ws], (wit / WS) & 1);
           tc_fence_after();
+
           const uint32_t w_base = smem_u32(wring + ws * W_STAGE);
 #pragma unroll
           for (int t = 0; t < 6; ++t) {
@@ -358,13 +365,12 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint64_t dw = make_smem_desc(w_base + pw[t] * (BN * T6_BK * 2));
             const int set = t < 5 ? 0 : 1 + kb % pm;
             const bool first = t < 5 ? (kb == 0 && t == 0) : (kb < pm);
-            // Issue pacing: one group of four MMAs per p.pace cycles, about the time the tensor pipe needs to
-            // execute it, so the queue in front of the pipe does not grow.  Issued as fast as the uniform datapath allows (~10 cycles
-            // per MMA), long bursts of these short MMAs came back with corrupted tiles, non-deterministically
-            // (tools/gemm6_stress.py); paced, the pipe is still never idle.
-            while (clock64() - t_grp < p.pace) {
+            // optional issue pacing (off by default, see T6 pacing note above)
+            if (p.pace > 0) {
+              while (clock64() - t_grp < p.pace) {
+              }
+              t_grp = clock64();
             }
-            t_grp = clock64();
 #pragma unroll
             for (int k = 0; k < T6_BK / 16; ++k)
               umma_bf16(acc_base + set * acc_stride + j * BN, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc,
@@ -397,10 +403,17 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             v[half * 8 + c] = (half == 0 || have2) ? *reinterpret_cast<const float4*>(src + ((c ^ sw) << 4))
                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        // The slot goes back to the TMA producer, i.e. the async proxy will overwrite what the generic proxy just
+        // read: that needs a proxy fence on this side as well, not only the mbarrier.  Without it whole tiles came
+        // back wrong (about one k-block's worth, ~1e-2), non-deterministically and only under memory contention
+        // (>= 64 CTAs) -- tools/gemm6_stress.py; an A/B build with only this fence added is clean.
+        fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&stg_empty[s]);      // staging slot may be refilled
-        mbar_wait(&pl_empty[s], ph ^ 1);                 // MMAs that read this plane buffer are done
-        uint8_t* dst = planes + s * 3 * T6_PLANE + r * 128;
+        const int ps = kit % NPL;
+        mbar_wait(&pl_empty[ps], ((kit / NPL) & 1) ^ 1);  // MMAs that read this plane buffer are done
+        fence_proxy_async();                              // async-proxy reads before the generic stores below
+        uint8_t* dst = planes + ps * 3 * T6_PLANE + r * 128;
         // Exact 3-way split by TRUNCATION: b1 = top 16 bits of x, r1 = x - b1 (exact), b2 = top 16 bits of
         // r1, r2 = r1 - b2 (exact), b3 = top 16 bits of r2 (r2 has <= 8 significant bits left, so b3 = r2).
         // No F2F conversions: one PRMT packs the upper halves of two floats into a bf16x2.
@@ -427,7 +440,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         fence_proxy_async();      // make the generic-proxy stores visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&pl_full[s]);
+        if (lane == 0) mbar_arrive(&pl_full[ps]);
       }
     }
   } else if (warp >= 4 + T6_CVT_WARPS) {
@@ -643,10 +656,10 @@ template <int BN, bool PRE>
 struct T6Cfg {
   static constexpr int W_STAGE = 3 * BN * T6_BK * 2;
   // f32 staging (2 x 32 KB) + two operand-plane buffers, or three plane buffers fed directly by TMA
-  static constexpr int FIXED = PRE ? T6_NPL_PRE * 3 * T6_PLANE : 2 * T6_STG + 2 * 3 * T6_PLANE;
+  static constexpr int FIXED = PRE ? T6_NPL_PRE * 3 * T6_PLANE : 2 * T6_STG + T6_NPL_F32 * 3 * T6_PLANE;
   static constexpr int SCRATCH = T6_EPI_WARPS * (PRE ? 8 : 16) * T6_SCR_LD * 4;
   static constexpr int WS_RAW = (232448 - 512 - FIXED - SCRATCH) / W_STAGE;
-  static constexpr int WS = WS_RAW > 4 ? 4 : WS_RAW;
+  static constexpr int WS = WS_RAW > 6 ? 6 : WS_RAW;
   static constexpr int SMEM = FIXED + WS * W_STAGE + SCRATCH + (16 + 2 * WS) * 8 + 16;   // barriers + tmem slot + last flag
   static_assert(SMEM <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static_assert(WS >= 2, "need at least two W stages");
@@ -667,8 +680,8 @@ static void launch6(const Tc6Gemm& g, cudaStream_t st) {
   p.m_tiles = p.t_tiles * ceil_div(g.B, g.b_sub);
   p.n_groups = ceil_div(g.N, g.nj * BN);
   p.split_k = g.split_k, p.ws = g.ws, p.counters = g.counters;
-  static const int pace64 = [] { const char* e = getenv("DSM_TC6_PACE64"); return e ? atoi(e) : T6_GROUP_CYCLES_64; }();
-  static const int pace32 = [] { const char* e = getenv("DSM_TC6_PACE32"); return e ? atoi(e) : T6_GROUP_CYCLES_32; }();
+  static const int pace64 = [] { const char* e = getenv("DSM_TC6_PACE64"); return e ? atoi(e) : 0; }();
+  static const int pace32 = [] { const char* e = getenv("DSM_TC6_PACE32"); return e ? atoi(e) : 0; }();
   p.pace = BN == 64 ? pace64 : pace32;
   p.bias = g.ep.bias, p.neg = g.ep.neg, p.scale = g.ep.scale, p.res = g.ep.res, p.r_map = g.ep.r_map, p.act = g.ep.act;
   p.out_raw = g.ep.out_raw, p.o_map = g.ep.o_map, p.out_act = g.ep.out_act, p.e_map = g.ep.e_map;
