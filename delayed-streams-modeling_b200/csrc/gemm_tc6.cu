@@ -101,6 +101,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lane = tile row, 32-bit column = two consecutive K elements), B from shared
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -178,6 +196,14 @@ constexpr int T6_THREADS = (4 + T6_CVT_WARPS + T6_EPI_WARPS) * 32;
 // Optional minimum spacing of the 4-MMA issue groups in cycles (DSM_TC6_PACE64/32; 0 = off, the default).  It was
 // the first, wrong, explanation of the corrupted tiles that the proxy fence in the converter warps cured; kept as
 // an A/B switch.
+#ifndef T6_TS
+#define T6_TS 1
+#endif
+// T6_TS: the f32-A variant keeps the converted A planes in TENSOR MEMORY (tcgen05.st by the converter warps, MMAs
+// with A from TMEM) instead of shared memory; the 96 KB go to a third staging slot and two more W stages.
+constexpr int T6_NSTG = T6_TS ? 3 : 2;           // f32 staging slots
+constexpr int T6_ACC_COLS_TS = 320;              // TMEM columns [0, 320): accumulators; [320, 512): two A buffers
+constexpr int T6_A_COLS = 96;                    // TMEM columns of one A buffer: 3 planes x 32 (64 bf16 per row)
 constexpr int T6_NPL_PRE = 3;        // operand-plane buffers of the pre-split variant (48 KB each)
 #ifndef T6_NPL_F32
 #define T6_NPL_F32 2
@@ -199,6 +225,7 @@ struct Tc6Params {
   int pm;              // main-term accumulators the k-blocks rotate over (see the MMA issuer)
   int split_k;         // K splits per tile (work item = (tile, split)); partials meet in `ws`
   int pace;            // minimum cycles between 4-MMA issue groups
+  int acc_bufs;        // accumulator tile buffers in TMEM (1 or 2)
   float* ws;           // [tiles * split_k][128][nj * BN] partial sums (split_k > 1)
   int* counters;       // [tiles] arrivals; the last split to arrive reduces in split order and stores
   const float* bias;
@@ -229,21 +256,23 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzle atoms need a 1024-byte aligned base
-  constexpr int NPL = PRE ? T6_NPL_PRE : T6_NPL_F32;      // operand-plane buffers
-  uint8_t* stg = smem;                           // [2][T6_STG]   (absent with PRE)
-  uint8_t* planes = stg + (PRE ? 0 : 2 * T6_STG);   // [NPL][3][T6_PLANE]
-  uint8_t* wring = planes + NPL * 3 * T6_PLANE;  // [WS][W_STAGE]
+  constexpr bool TS = !PRE && T6_TS;             // A planes in tensor memory
+  constexpr int NPL = PRE ? T6_NPL_PRE : (TS ? 2 : T6_NPL_F32);      // operand-plane buffers (TS: in TMEM)
+  constexpr int NSTG = T6_NSTG;
+  uint8_t* stg = smem;                           // [NSTG][T6_STG]   (absent with PRE)
+  uint8_t* planes = stg + (PRE ? 0 : NSTG * T6_STG);   // [NPL][3][T6_PLANE]   (absent with TS)
+  uint8_t* wring = planes + (TS ? 0 : NPL * 3 * T6_PLANE);  // [WS][W_STAGE]
   constexpr int SR = PRE ? 8 : 16;               // rows of one epilogue warp's transposition tile
   constexpr int PARTS = 32 / SR, QN = SR / 4;
   float* scratch_all = reinterpret_cast<float*>(wring + WS * W_STAGE);   // [epilogue warps][SR][36]
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch_all + T6_EPI_WARPS * SR * T6_SCR_LD);
-  uint64_t* stg_full = bars;             // [2]
-  uint64_t* stg_empty = bars + 2;        // [2]
-  uint64_t* pl_full = bars + 4;          // [NPL <= 4]
-  uint64_t* pl_empty = bars + 8;         // [NPL <= 4]
-  uint64_t* acc_full = bars + 12;        // [2]
-  uint64_t* acc_empty = bars + 14;       // [2]
-  uint64_t* w_full = bars + 16;          // [WS]
+  uint64_t* stg_full = bars;             // [NSTG <= 4]
+  uint64_t* stg_empty = bars + 4;        // [NSTG <= 4]
+  uint64_t* pl_full = bars + 8;          // [NPL <= 4]
+  uint64_t* pl_empty = bars + 12;        // [NPL <= 4]
+  uint64_t* acc_full = bars + 16;        // [2]
+  uint64_t* acc_empty = bars + 18;       // [2]
+  uint64_t* w_full = bars + 20;          // [WS]
   uint64_t* w_empty = w_full + WS;       // [WS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + WS);
   uint32_t* last_flag = tmem_slot + 1;
@@ -252,7 +281,8 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int num_kb = (p.K + T6_BK - 1) / T6_BK;
   const int rows_box = p.t_sub * p.b_sub;
   const int acc_stride = p.nj * BN;          // columns of one accumulator set
-  const int buf_stride = (1 + p.pm) * acc_stride;   // columns of one tile's accumulators (<= 256)
+  const int buf_stride = (1 + p.pm) * acc_stride;   // columns of one tile's accumulators
+  const int AB = p.acc_bufs;                        // 2: the epilogue of tile i overlaps the MMAs of tile i+1
   const int total_tiles = p.m_tiles * p.n_groups;
   const int S = p.split_k;
   const int kb_per = (num_kb + S - 1) / S;       // the host picks S so that no split is empty
@@ -267,9 +297,11 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_init(&pl_full[s], PRE ? 1 : T6_CVT_WARPS);
       mbar_init(&pl_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NSTG; ++s) {
       mbar_init(&stg_full[s], 1);
       mbar_init(&stg_empty[s], T6_CVT_WARPS);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], T6_EPI_WARPS);
     }
@@ -302,8 +334,8 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             tma_load_4d(planes + (s * 3 + q) * T6_PLANE, &map_a, kb * T6_BK, t0, b0, q, &pl_full[s]);
           continue;
         }
-        const int s = kit & 1;
-        mbar_wait(&stg_empty[s], ((kit >> 1) & 1) ^ 1);
+        const int s = kit % NSTG;
+        mbar_wait(&stg_empty[s], ((kit / NSTG) & 1) ^ 1);
         const int kc = kb * T6_BK;
         const int nsub = (p.K - kc > 32) ? 2 : 1;
         mbar_expect_tx(&stg_full[s], (uint32_t)(nsub * rows_box * 128));
@@ -344,15 +376,15 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int pm = min(p.pm, kbn);                       // main accumulators actually written
       const int n0 = (tile % p.n_groups) * p.nj * BN;
       const int nj = min(p.nj, (p.N - n0 + BN - 1) / BN);
-      const int buf = li & 1;
-      mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1);     // epilogue has drained this TMEM buffer
+      const int buf = li % AB;
+      mbar_wait(&acc_empty[buf], ((li / AB) & 1) ^ 1);     // epilogue has drained this TMEM buffer
       tc_fence_after();
       const uint32_t acc_base = tmem_base + buf * buf_stride;
       for (int kb = 0; kb < kbn; ++kb, ++kit) {
         const int s = kit % NPL;
         mbar_wait(&pl_full[s], (kit / NPL) & 1);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(planes + s * 3 * T6_PLANE);
+        const uint32_t a_base = TS ? tmem_base + T6_ACC_COLS_TS + s * T6_A_COLS : smem_u32(planes + s * 3 * T6_PLANE);
         for (int j = 0; j < nj; ++j, ++wit) {
           const int ws = wit % WS;
           mbar_wait(&w_full[ws], (wit / WS) & 1);
@@ -372,9 +404,14 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               t_grp = clock64();
             }
 #pragma unroll
-            for (int k = 0; k < T6_BK / 16; ++k)
-              umma_bf16(acc_base + set * acc_stride + j * BN, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc,
-                        (first && k == 0) ? 0u : 1u);
+            for (int k = 0; k < T6_BK / 16; ++k) {
+              if (TS)
+                umma_bf16_ts(acc_base + set * acc_stride + j * BN, a_base + pa[t] * 32 + k * 8, dw + (uint64_t)(k * 2), idesc,
+                             (first && k == 0) ? 0u : 1u);
+              else
+                umma_bf16(acc_base + set * acc_stride + j * BN, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc,
+                          (first && k == 0) ? 0u : 1u);
+            }
           }
           umma_commit(&w_empty[ws]);
         }
@@ -390,8 +427,8 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int kb0 = (item % S) * kb_per, kbn = min(kb_per, num_kb - kb0);
       for (int kb = kb0; kb < kb0 + kbn; ++kb, ++kit) {
-        const int s = kit & 1;
-        const uint32_t ph = (kit >> 1) & 1;
+        const int s = kit % NSTG;
+        const uint32_t ph = (kit / NSTG) & 1;
         const bool have2 = p.K - kb * T6_BK > 32;      // second 32-wide half present
         float4 v[16];
         mbar_wait(&stg_full[s], ph);
@@ -412,8 +449,12 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (lane == 0) mbar_arrive(&stg_empty[s]);      // staging slot may be refilled
         const int ps = kit % NPL;
         mbar_wait(&pl_empty[ps], ((kit / NPL) & 1) ^ 1);  // MMAs that read this plane buffer are done
-        fence_proxy_async();                              // async-proxy reads before the generic stores below
+        if (TS) tc_fence_after();
+        else fence_proxy_async();                         // async-proxy reads before the generic stores below
         uint8_t* dst = planes + ps * 3 * T6_PLANE + r * 128;
+        // TS: thread r owns TMEM lane r (the converter warps 4..7 reach lane quadrants 0..3); 32 columns per plane
+        const uint32_t tdst = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + T6_ACC_COLS_TS + ps * T6_A_COLS;
+        uint32_t h1[4], h2[4], h3[4];
         // Exact 3-way split by TRUNCATION: b1 = top 16 bits of x, r1 = x - b1 (exact), b2 = top 16 bits of
         // r1, r2 = r1 - b2 (exact), b3 = top 16 bits of r2 (r2 has <= 8 significant bits left, so b3 = r2).
         // No F2F conversions: one PRMT packs the upper halves of two floats into a bf16x2.
@@ -433,12 +474,32 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const float s0 = r0 - __uint_as_float(v0 & 0xffff0000u), s1 = r1 - __uint_as_float(v1 & 0xffff0000u);
             p3[e] = __byte_perm(__float_as_uint(s0), __float_as_uint(s1), 0x7632);
           }
-          const int chunk = (cc ^ sw) << 4;
-          *reinterpret_cast<uint4*>(dst + chunk) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-          *reinterpret_cast<uint4*>(dst + T6_PLANE + chunk) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
-          *reinterpret_cast<uint4*>(dst + 2 * T6_PLANE + chunk) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
+          if (TS) {
+            // eight floats -> four packed columns per plane; stored eight columns at a time
+            if (cc & 1) {
+              uint32_t q1[8] = {h1[0], h1[1], h1[2], h1[3], p1[0], p1[1], p1[2], p1[3]};
+              uint32_t q2[8] = {h2[0], h2[1], h2[2], h2[3], p2[0], p2[1], p2[2], p2[3]};
+              uint32_t q3[8] = {h3[0], h3[1], h3[2], h3[3], p3[0], p3[1], p3[2], p3[3]};
+              tmem_st8(tdst + (cc - 1) * 4, q1);
+              tmem_st8(tdst + 32 + (cc - 1) * 4, q2);
+              tmem_st8(tdst + 64 + (cc - 1) * 4, q3);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h1[e] = p1[e], h2[e] = p2[e], h3[e] = p3[e];
+            }
+          } else {
+            const int chunk = (cc ^ sw) << 4;
+            *reinterpret_cast<uint4*>(dst + chunk) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+            *reinterpret_cast<uint4*>(dst + T6_PLANE + chunk) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+            *reinterpret_cast<uint4*>(dst + 2 * T6_PLANE + chunk) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
+          }
         }
-        fence_proxy_async();      // make the generic-proxy stores visible to the tensor core (async proxy)
+        if (TS) {
+          tmem_st_wait();
+          tc_fence_before();
+        } else {
+          fence_proxy_async();      // make the generic-proxy stores visible to the tensor core (async proxy)
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&pl_full[ps]);
       }
@@ -473,8 +534,8 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const uint32_t act_off = p.out_act ? (uint32_t)p.e_map.off(m) : 0u;
       const uint32_t pl_off = p.out_pl ? (uint32_t)p.pl_map.off(m) : 0u;
       const uint32_t ok_mask = __ballot_sync(0xffffffffu, row_ok);
-      const int buf = li & 1;
-      mbar_wait(&acc_full[buf], (li >> 1) & 1);
+      const int buf = li % AB;
+      mbar_wait(&acc_full[buf], (li / AB) & 1);
       tc_fence_after();
       const uint32_t acc_addr = lane_addr + buf * buf_stride;
       const int n_chunks = nj * BN / 32;
@@ -656,11 +717,12 @@ template <int BN, bool PRE>
 struct T6Cfg {
   static constexpr int W_STAGE = 3 * BN * T6_BK * 2;
   // f32 staging (2 x 32 KB) + two operand-plane buffers, or three plane buffers fed directly by TMA
-  static constexpr int FIXED = PRE ? T6_NPL_PRE * 3 * T6_PLANE : 2 * T6_STG + T6_NPL_F32 * 3 * T6_PLANE;
+  static constexpr int FIXED = PRE ? T6_NPL_PRE * 3 * T6_PLANE
+                                   : T6_NSTG * T6_STG + (T6_TS ? 0 : T6_NPL_F32 * 3 * T6_PLANE);
   static constexpr int SCRATCH = T6_EPI_WARPS * (PRE ? 8 : 16) * T6_SCR_LD * 4;
   static constexpr int WS_RAW = (232448 - 512 - FIXED - SCRATCH) / W_STAGE;
   static constexpr int WS = WS_RAW > 6 ? 6 : WS_RAW;
-  static constexpr int SMEM = FIXED + WS * W_STAGE + SCRATCH + (16 + 2 * WS) * 8 + 16;   // barriers + tmem slot + last flag
+  static constexpr int SMEM = FIXED + WS * W_STAGE + SCRATCH + (20 + 2 * WS) * 8 + 16;   // barriers + tmem slot + last flag
   static_assert(SMEM <= 232448, "exceeds the 227 KB shared-memory limit per CTA");
   static_assert(WS >= 2, "need at least two W stages");
 };
@@ -683,6 +745,7 @@ static void launch6(const Tc6Gemm& g, cudaStream_t st) {
   static const int pace64 = [] { const char* e = getenv("DSM_TC6_PACE64"); return e ? atoi(e) : 0; }();
   static const int pace32 = [] { const char* e = getenv("DSM_TC6_PACE32"); return e ? atoi(e) : 0; }();
   p.pace = BN == 64 ? pace64 : pace32;
+  p.acc_bufs = g.acc_bufs;
   p.bias = g.ep.bias, p.neg = g.ep.neg, p.scale = g.ep.scale, p.res = g.ep.res, p.r_map = g.ep.r_map, p.act = g.ep.act;
   p.out_raw = g.ep.out_raw, p.o_map = g.ep.o_map, p.out_act = g.ep.out_act, p.e_map = g.ep.e_map;
   p.out_pl = g.ep.out_planes, p.pl_map = g.ep.p_map, p.pl_stride = g.ep.out_plane_stride;
@@ -761,12 +824,23 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes,
   // column sub-tiles per CTA: as many as TMEM holds (512 columns) while the grid still covers the SMs
   // (TMEM: two tile buffers of 256 columns, each shared by the correction accumulator and >= 1 main
   // accumulator => at most 128 output columns per tile)
-  static const int max_tile_n = [] { const char* e = getenv("DSM_TC6_TILE_N"); int v = e ? atoi(e) : 0; return v >= 32 ? v : 128; }();
+  static const int max_tile_n = [] { const char* e = getenv("DSM_TC6_TILE_N"); int v = e ? atoi(e) : 0; return v >= 32 ? v : (T6_TS ? 64 : 128); }();
   // pre-split A: one column sub-tile per CTA keeps the W ring as deep (in k-blocks) as the operand ring
   int nj = std::max(1, std::min(n_sub, std::min(g.a_planes ? 64 : 128, max_tile_n) / t.bn));
   while (nj > 1 && m_tiles * ceil_div(n_sub, nj) < 148) nj = (nj + 1) / 2;
   t.nj = nj;
-  t.pm = std::max(1, std::min(7, 256 / (nj * t.bn) - 1));
+  // TMEM: 512 accumulator columns, or 320 when the A planes live in tensor memory (f32-A variant).  Two tile
+  // buffers when they fit with at least one main accumulator beside the correction accumulator; long K loops
+  // (> 8 k-blocks) want more rotating accumulators than that leaves and take the whole region as one buffer
+  // (the tensor core truncates when it accumulates: see the MMA issuer).
+  {
+    const bool ts = T6_TS && !g.a_planes;
+    const int acc_cols = ts ? T6_ACC_COLS_TS : 512;
+    const int tile_n = nj * t.bn;
+    const bool long_k = ts && ceil_div(g.K, T6_BK) > 8;
+    t.acc_bufs = (!long_k && 2 * 2 * tile_n <= acc_cols) ? 2 : 1;
+    t.pm = std::max(1, std::min(7, acc_cols / (t.acc_bufs * tile_n) - 1));
+  }
   // Skinny problems (few tiles, long K) cannot fill 148 SMs with tiles alone: split K over several CTAs
   // per tile; the partial sums meet in the shared workspace and the last arrival reduces them in order.
   {

@@ -24,7 +24,7 @@ struct Tc6Gemm {
   CUtensorMap map_a;   // f32 [B][T_out][K] window view of the activation buffer
   CUtensorMap map_w;   // bf16 [3][N][K] pre-split weight planes
   int K = 0, N = 0, T_out = 0, B = 0;
-  int t_sub = 0, b_sub = 0, bn = 0, nj = 0, pm = 1, split_k = 1;
+  int t_sub = 0, b_sub = 0, bn = 0, nj = 0, pm = 1, split_k = 1, acc_bufs = 2;
   bool presplit = false;   // A arrives as bf16 planes (GemmParams::a_planes): TMA feeds the operand buffers directly
   float* ws = nullptr;
   int* counters = nullptr;
