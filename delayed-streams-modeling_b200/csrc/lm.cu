@@ -340,7 +340,7 @@ AsrImpl::AsrImpl(MimiImpl* mi, LmImpl* l, int dly, float temperature) : mimi(mi)
   h_prs = static_cast<float*>(arena.alloc_pinned((size_t)std::max(nh, 1) * B * 4));
   h_mask.assign(B, 1);
   items.resize(B);
-  for (cudaEvent_t* e : {&ev_fork, &ev_join}) DSM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  for (cudaEvent_t* e : {&ev_fork, &ev_join, &ev_seanet}) DSM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   for (cudaEvent_t* e : {&ev_t0, &ev_t1, &ev_m0, &ev_m1, &ev_l0, &ev_l1}) DSM_CUDA(cudaEventCreate(e));
   reset();
 }
@@ -351,7 +351,7 @@ AsrImpl::~AsrImpl() {
   if (mimi) cudaStreamSynchronize(mimi->stream);
   graph_pcm.reset();
   graph_tokens.reset();
-  for (cudaEvent_t e : {ev_fork, ev_join, ev_t0, ev_t1, ev_m0, ev_m1, ev_l0, ev_l1})
+  for (cudaEvent_t e : {ev_fork, ev_join, ev_seanet, ev_t0, ev_t1, ev_m0, ev_m1, ev_l0, ev_l1})
     if (e) cudaEventDestroy(e);
 }
 
@@ -397,7 +397,18 @@ void AsrImpl::enqueue(bool with_mimi, bool timing) {
     DSM_CUDA(cudaEventRecord(ev_fork, sl));
     DSM_CUDA(cudaStreamWaitEvent(sm, ev_fork, 0));
     if (timing) DSM_CUDA(cudaEventRecord(ev_m0, sm));
-    run_plan(mimi->enc_plan, sm);
+    // DSM_ASR_SEANET_FIRST=1: the LM branch starts only when the SEANet encoder is through.  Its GEMMs take every
+    // SM (persistent 148-CTA grids) and the LM's attention takes every byte of HBM bandwidth; run side by side they
+    // only get in each other's way, while the codec's transformer and RVQ (few CTAs per launch) do overlap the LM.
+    static const bool seanet_first = [] { const char* e = getenv("DSM_ASR_SEANET_FIRST"); return e && e[0] == '1'; }();
+    if (seanet_first && mimi->enc_seanet_end > 0 && mimi->enc_seanet_end < mimi->enc_plan.size()) {
+      for (size_t i = 0; i < mimi->enc_seanet_end; ++i) mimi->enc_plan[i](sm);
+      DSM_CUDA(cudaEventRecord(ev_seanet, sm));
+      DSM_CUDA(cudaStreamWaitEvent(sl, ev_seanet, 0));
+      for (size_t i = mimi->enc_seanet_end; i < mimi->enc_plan.size(); ++i) mimi->enc_plan[i](sm);
+    } else {
+      run_plan(mimi->enc_plan, sm);
+    }
     if (timing) DSM_CUDA(cudaEventRecord(ev_m1, sm));
     DSM_CUDA(cudaEventRecord(ev_join, sm));
   }

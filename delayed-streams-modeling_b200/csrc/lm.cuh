@@ -112,7 +112,7 @@ struct AsrImpl {
   std::vector<ItemState> items;
   std::vector<AsrMsgStore> msgs;
   std::vector<float> prs_copy;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_m0 = nullptr, ev_m1 = nullptr,
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_seanet = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_m0 = nullptr, ev_m1 = nullptr,
               ev_l0 = nullptr, ev_l1 = nullptr;
   GraphExec graph_pcm, graph_tokens;
   float last_ms[3] = {-1.f, -1.f, -1.f};

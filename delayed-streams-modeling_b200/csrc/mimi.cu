@@ -490,6 +490,7 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
 
   SeanetBuild sb{this, &arena, B, &get, &wt, &enc_plan, &enc_commits};
   build_seanet(sb, L, DSM_FRAME_SIZE, nullptr, x, x_map, d_pcm, enc_state0, nullptr);
+  enc_seanet_end = enc_plan.size();
 
   const int Bc = B;
   const size_t row_bytes = (size_t)D * sizeof(float);
