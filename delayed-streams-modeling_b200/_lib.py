@@ -57,6 +57,13 @@ class AsrMsgC(C.Structure):
                 ("tokens", C.POINTER(C.c_uint32)), ("time", C.c_double), ("prs", C.POINTER(C.c_float))]
 
 
+class LmOptionsC(C.Structure):
+    _fields_ = [("kv_dtype", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+KV_BF16, KV_INT8, KV_INT8K = 0, 1, 2
+
+
 class SchedOutC(C.Structure):
     _fields_ = [("kind", C.c_int32), ("slot", C.c_int32), ("channel_id", C.c_uint64), ("step_idx", C.c_int32),
                 ("n_tokens", C.c_int32), ("tokens", C.POINTER(C.c_uint32)), ("time", C.c_double), ("n_prs", C.c_int32),
@@ -77,6 +84,7 @@ SIGNATURES = {
     "dsm_debug_gemm_bf16": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "dsm_debug_gemm_f32": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P,
                                        C.c_int64, _P, _P, _P]),
+    "dsm_debug_ring_trace": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "dsm_mimi_spec_v0_1": (None, [C.POINTER(MimiSpecC), C.c_int32]),
     "dsm_lm_spec_stt_1b_en_fr": (None, [C.POINTER(LmSpecC)]),
     "dsm_lm_spec_stt_2_6b_en": (None, [C.POINTER(LmSpecC)]),
@@ -94,6 +102,9 @@ SIGNATURES = {
     "dsm_mimi_device_bytes": (C.c_int64, [_P]),
     "dsm_mimi_kv_bytes": (C.c_int64, [_P]),
     "dsm_lm_create": (C.c_int32, [C.POINTER(LmSpecC), C.POINTER(Weights), C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "dsm_lm_create_ex": (C.c_int32, [C.POINTER(LmSpecC), C.POINTER(Weights), C.c_int32, C.c_int32, C.POINTER(LmOptionsC),
+                                     C.POINTER(_P)]),
+    "dsm_lm_kv_dtype": (C.c_int32, [_P]),
     "dsm_lm_destroy": (None, [_P]),
     "dsm_lm_forward": (C.c_int32, [_P, _P, _P, _P, _P, _P, _P]),
     "dsm_lm_reset_state": (C.c_int32, [_P]),

@@ -131,14 +131,22 @@ class Mimi:
 class LmModel:
     """``LmModel::batched`` (lm.rs:812-897) without depformer."""
 
-    def __init__(self, spec: LmSpec, weights: Optional[Dict[str, np.ndarray]], batch_size: int, device: int = 0):
+    KV_DTYPES = {"bf16": _lib.KV_BF16, "int8": _lib.KV_INT8, "int8k": _lib.KV_INT8K}
+
+    def __init__(self, spec: LmSpec, weights: Optional[Dict[str, np.ndarray]], batch_size: int, device: int = 0,
+                 kv_dtype: str = "bf16"):
+        """``kv_dtype``: storage of the ring KV cache, "bf16" (the reference's, default), "int8" (opt-in, half the
+        bytes) or "int8k" (opt-in, int8 K + bf16 V); see ``dsm_lm_options`` in the header."""
         self._lib = _lib.load()
         self.spec, self.batch_size, self.device = spec, batch_size, device
         self._h = C.c_void_p()
         table = _lib.WeightTable(weights) if weights is not None else None
         c = lm_spec_c(spec)
-        check(self._lib.dsm_lm_create(C.byref(c), C.byref(table.c) if table else None, device, batch_size,
-                                      C.byref(self._h)))
+        opt = _lib.LmOptionsC()
+        opt.kv_dtype = self.KV_DTYPES[kv_dtype]
+        self.kv_dtype = kv_dtype
+        check(self._lib.dsm_lm_create_ex(C.byref(c), C.byref(table.c) if table else None, device, batch_size,
+                                         C.byref(opt), C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

@@ -214,6 +214,37 @@ dsm_status dsm_debug_gemm_f32(int32_t impl, int32_t B, int32_t T, int64_t stride
   });
 }
 
+dsm_status dsm_debug_ring_trace(int32_t batch, int32_t context, int32_t n_steps, const int32_t* t, const uint8_t* masks,
+                                uint32_t* indices_out, float* mask_out) {
+  return guarded([&] {
+    REQUIRE(batch > 0 && context > 0 && n_steps >= 0 && t && masks && indices_out && mask_out, "invalid arguments");
+    require_device(0);
+    DSM_CUDA(cudaSetDevice(0));
+    Arena a;
+    RingState rs;
+    rs.positions = a.alloc<uint32_t>(batch), rs.indices = a.alloc<uint32_t>(batch);
+    rs.cur_index = a.alloc<uint32_t>(batch), rs.cur_pos = a.alloc<uint32_t>(batch), rs.rope_pos = a.alloc<uint32_t>(batch);
+    uint8_t* d_mask = a.alloc<uint8_t>(batch);
+    int t_max = 1;
+    for (int i = 0; i < n_steps; ++i) {
+      DSM_CHECK(t[i] > 0 && t[i] < context, DSM_ERR_INVALID_ARG, "step %d: t=%d outside (0, context)", i, t[i]);
+      t_max = std::max(t_max, t[i]);
+    }
+    uint32_t* d_idx = a.alloc<uint32_t>((size_t)batch * t_max);
+    float* d_am = a.alloc<float>((size_t)batch * t_max * context);
+    for (int i = 0; i < n_steps; ++i) {
+      DSM_CUDA(cudaMemcpy(d_mask, masks + (size_t)i * batch, batch, cudaMemcpyHostToDevice));
+      launch_ring_advance(rs, d_mask, batch, t[i], context, 0);
+      launch_ring_debug(rs, d_mask, batch, t[i], context, d_idx, d_am, 0);
+      DSM_CUDA(cudaDeviceSynchronize());
+      DSM_CUDA(cudaMemcpy(indices_out, d_idx, (size_t)batch * t[i] * 4, cudaMemcpyDeviceToHost));
+      DSM_CUDA(cudaMemcpy(mask_out, d_am, (size_t)batch * t[i] * context * 4, cudaMemcpyDeviceToHost));
+      indices_out += (size_t)batch * t[i];
+      mask_out += (size_t)batch * t[i] * context;
+    }
+  });
+}
+
 // ---- Mimi ----------------------------------------------------------------------------------------
 dsm_status dsm_mimi_create(const dsm_mimi_spec* spec, const dsm_weights* weights, int32_t device, int32_t batch_size,
                            dsm_mimi** out) {
@@ -313,6 +344,17 @@ dsm_status dsm_lm_create(const dsm_lm_spec* spec, const dsm_weights* weights, in
     *out = new dsm_lm{impl.release()};
   });
 }
+dsm_status dsm_lm_create_ex(const dsm_lm_spec* spec, const dsm_weights* weights, int32_t device, int32_t batch_size,
+                            const dsm_lm_options* options, dsm_lm** out) {
+  return guarded([&] {
+    REQUIRE(spec && out, "spec and out are required");
+    *out = nullptr;
+    require_device(device);
+    std::unique_ptr<LmImpl> impl(new LmImpl(*spec, weights, device, batch_size, options));
+    *out = new dsm_lm{impl.release()};
+  });
+}
+int32_t dsm_lm_kv_dtype(const dsm_lm* h) { return h ? h->impl->kv_dtype : -1; }
 void dsm_lm_destroy(dsm_lm* h) {
   if (!h) return;
   delete h->impl;

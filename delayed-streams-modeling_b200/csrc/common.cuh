@@ -69,6 +69,21 @@ struct RowMap {
 };
 inline RowMap dense_rows(int T, long long row_len) { return RowMap{T, (long long)T * row_len, row_len}; }
 
+// cudaFuncSetAttribute is per DEVICE: remembers on which devices a kernel has been configured (a handle may live on
+// any GPU of the process).  The configuring call is idempotent, so a race between two threads is benign.
+struct PerDeviceOnce {
+  unsigned long long done = 0;
+  template <typename F>
+  void run(F&& f) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ULL << (dev & 63);
+    if (__atomic_load_n(&done, __ATOMIC_ACQUIRE) & bit) return;
+    f();
+    __atomic_fetch_or(&done, bit, __ATOMIC_RELEASE);
+  }
+};
+
 template <typename T>
 inline T ceil_div(T a, T b) {
   return (a + b - 1) / b;

@@ -43,6 +43,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// thread-block cluster helpers (split-K partials meet through distributed shared memory)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -126,6 +143,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 constexpr int TC_BN = 128;      // weight rows per CTA (UMMA M)
 constexpr int TC_BK = 64;       // bf16 per k-block = one 128-byte swizzle row
 constexpr int TC_UK = 16;       // UMMA K for 16-bit inputs
+constexpr int TC_MAX_SPLIT = 8; // split-K = cluster size (portable maximum)
 
 struct TcParams {
   int M, N, K;
@@ -134,7 +152,6 @@ struct TcParams {
   int hidden;
   float* out_f32;
   __nv_bfloat16* out_bf16;
-  int atomic;        // ACCUM with split-K: combine with red.global.add.f32
 };
 
 // NACC weight sub-tiles (accumulators) per CTA: the gate/value pair, or two consecutive 128-row tiles
@@ -245,7 +262,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         }
       }
     }
-  } else {
+  } else if (gridDim.z == 1) {
 #pragma unroll 1
     for (int a = 0; a < NACC; ++a) {
       const int n = n0 + a * TC_BN + warp * 32 + lane;       // this thread's weight row in sub-tile a
@@ -260,12 +277,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             const int m = m0 + c + i;
             if (m < p.M) {
               float* dst = p.out_f32 + (long long)m * p.N + n;
-              if (p.atomic) atomicAdd(dst, v[i]);
-              else if (MODE == TC_STORE_F32) *dst = v[i];
+              if (MODE == TC_STORE_F32) *dst = v[i];
               else *dst += v[i];
             }
           }
         }
+      }
+    }
+  } else {
+    // Split-K (NACC == 1): the gridDim.z CTAs of a tile form a thread-block cluster.  Each keeps its partial tile
+    // in TMEM, and once every CTA of the cluster is through its K loop (the pipeline stages are then free) pushes
+    // it -- st.shared::cluster, fire and forget -- into the shared memory of the CTA that owns the stream slice:
+    // rank r reduces streams [r*BMX/S, (r+1)*BMX/S) of the tile, adding the S partials IN RANK ORDER (the same sum
+    // in every run, unlike f32 atomics on the output), and applies the epilogue.  No global workspace, no spinning.
+    const uint32_t S = gridDim.z, rank = cluster_ctarank();
+    const uint32_t slice_max = (BMX + S - 1) / S;
+    const int row = warp * 32 + lane;
+    float* buf = reinterpret_cast<float*>(smem);            // [S][slice_max][128] partials of MY slice
+    cluster_sync();                                         // every CTA is done with its stages
+#pragma unroll 1
+    for (int c = 0; c < BMX; c += 32) {
+      if (m0 + c >= p.M) break;
+      float v[32];
+      tmem_ld32(lane_addr + c, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const uint32_t mm = c + i;
+        uint32_t owner = mm * S / BMX;                      // slice r = streams [ceil(r*BMX/S), ceil((r+1)*BMX/S))
+        if (((owner + 1) * BMX + S - 1) / S <= mm) ++owner;
+        const uint32_t local = mm - (owner * BMX + S - 1) / S;
+        st_cluster_f32(map_to_rank(smem_u32(buf + ((size_t)rank * slice_max + local) * TC_BN + row), owner), v[i]);
+      }
+    }
+    cluster_sync();                                         // all partials have landed
+    const int n = n0 + row;
+    const uint32_t mm0 = (rank * BMX + S - 1) / S, mm1 = ((rank + 1) * BMX + S - 1) / S;
+    if (n < p.N) {
+#pragma unroll 4
+      for (uint32_t mm = mm0; mm < mm1; ++mm) {
+        if (m0 + (int)mm >= p.M) break;
+        float acc = 0.f;
+        for (uint32_t sp = 0; sp < S; ++sp) acc += buf[((size_t)sp * slice_max + (mm - mm0)) * TC_BN + row];
+        float* dst = p.out_f32 + (long long)(m0 + mm) * p.N + n;
+        if (MODE == TC_STORE_F32) *dst = acc;
+        else *dst += acc;
       }
     }
   }
@@ -319,30 +374,63 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = NACC * TC_BN * TC_BK * 2 + BMX * TC_BK * 2;
   static constexpr int RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = RAW > 8 ? 8 : RAW;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;   // barriers, tmem slot, last flag
 };
 
 template <int BMX, int MODE, int NACC>
 static void launch_tc(const TcGemm& g, cudaStream_t st) {
   using C = TcCfg<BMX, MODE, NACC>;
   auto kern = tc_gemm_kernel<BMX, MODE, NACC, C::STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr;
+  attr.run([&] { DSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); });
   TcParams p;
   p.M = g.M, p.N = g.N, p.K = g.K, p.hidden = g.hidden;
   p.kb_total = g.K / TC_BK;
   p.kb_per_split = ceil_div(p.kb_total, g.split_k);
   DSM_CHECK(ceil_div(p.kb_total, p.kb_per_split) == g.split_k, DSM_ERR_INVALID_ARG, "tc_gemm: split_k %d leaves an empty split", g.split_k);
-  p.out_f32 = g.out_f32, p.out_bf16 = g.out_bf16, p.atomic = g.split_k > 1;
+  p.out_f32 = g.out_f32, p.out_bf16 = g.out_bf16;
   const int n_rows = MODE == TC_GATE_BF16 ? g.hidden : g.N;
   dim3 grid(ceil_div(n_rows, TC_BN * (MODE == TC_GATE_BF16 ? 1 : NACC)), ceil_div(g.M, BMX), g.split_k);
-  if (MODE == TC_STORE_F32 && g.split_k > 1)   // partial sums are combined by atomics onto zeros
-    DSM_CUDA(cudaMemsetAsync(g.out_f32, 0, (size_t)g.M * g.N * sizeof(float), st));
-  kern<<<grid, 128, C::SMEM, st>>>(g.map_w, g.map_x, p);
+  DSM_CHECK(g.split_k == 1 || (NACC == 1 && g.split_k <= TC_MAX_SPLIT), DSM_ERR_INVALID_ARG, "tc_gemm: split_k %d", g.split_k);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = dim3(128), cfg.dynamicSmemBytes = C::SMEM, cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  if (g.split_k > 1) {
+    attrs[0].id = cudaLaunchAttributeClusterDimension;     // the splits of a tile are one cluster
+    attrs[0].val.clusterDim.x = 1, attrs[0].val.clusterDim.y = 1, attrs[0].val.clusterDim.z = (unsigned)g.split_k;
+    cfg.attrs = attrs, cfg.numAttrs = 1;
+  }
+  DSM_CUDA(cudaLaunchKernelEx(&cfg, kern, g.map_w, g.map_x, p));
   check_launch("tc_gemm");
+}
+
+// Clusters of `split` CTAs of this configuration the device can hold at once.
+template <int BMX, int MODE>
+static int cluster_capacity(int split) {
+  using C = TcCfg<BMX, MODE, 1>;
+  auto kern = tc_gemm_kernel<BMX, MODE, 1, C::STAGES>;
+  static PerDeviceOnce attr;
+  attr.run([&] { DSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); });
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1, 1, split), cfg.blockDim = dim3(128), cfg.dynamicSmemBytes = C::SMEM;
+  cudaLaunchAttribute a[1];
+  a[0].id = cudaLaunchAttributeClusterDimension;
+  a[0].val.clusterDim.x = 1, a[0].val.clusterDim.y = 1, a[0].val.clusterDim.z = (unsigned)split;
+  cfg.attrs = a, cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+static int tc_cluster_capacity(int bmx, int mode, int split) {
+#define CAP_CASE(BMX, MODE) \
+  if (bmx == BMX && mode == MODE) return cluster_capacity<BMX, MODE>(split);
+  CAP_CASE(64, TC_STORE_F32) CAP_CASE(128, TC_STORE_F32) CAP_CASE(256, TC_STORE_F32)
+  CAP_CASE(64, TC_ACCUM_F32) CAP_CASE(128, TC_ACCUM_F32) CAP_CASE(256, TC_ACCUM_F32)
+#undef CAP_CASE
+  return 0;
 }
 
 void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, int M, int N, int K, int mode,
@@ -360,25 +448,30 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
   const int n_tiles = ceil_div(n_rows, TC_BN * (mode == TC_GATE_BF16 ? 1 : g.nacc));
   // Stream tile: as wide as the batch allows.  Every CTA must pull its W slab AND its X slab through
   // the SM's L2 port, so narrower stream tiles multiply the X traffic; to cover the 148 SMs we split K
-  // instead (same total bytes, more CTAs) and combine the partial sums with f32 atomics.  The gate
-  // pair has a non-linear epilogue, so it does not split.
+  // instead (same total bytes, more CTAs): the splits of a tile form a cluster and add their partial tiles
+  // through distributed shared memory in rank order (deterministic).  The gate pair has a non-linear epilogue, so it does not split.
   g.bmx = M <= 64 ? 64 : (M <= 128 ? 128 : ((mode == TC_GATE_BF16 && !wide) ? 128 : 256));
   // experiment knobs: DSM_TC_BMX forces the stream tile, DSM_TC_MAXSPLIT caps split-K
   static const int env_bmx = [] { const char* e = getenv("DSM_TC_BMX"); return e ? atoi(e) : 0; }();
-  static const int env_split = [] { const char* e = getenv("DSM_TC_MAXSPLIT"); return e ? atoi(e) : 16; }();
+  static const int env_split = [] { const char* e = getenv("DSM_TC_MAXSPLIT"); return e ? std::min(atoi(e), TC_MAX_SPLIT) : TC_MAX_SPLIT; }();
   if (env_bmx && mode != TC_GATE_BF16 && M > env_bmx / 2) g.bmx = env_bmx;
   g.split_k = 1;
-  if (mode != TC_GATE_BF16) {
+  if (mode != TC_GATE_BF16 && g.nacc == 1) {
+    // Pick the split by a cost model in k-block units: a CTA costs a fixed prologue + pipeline fill + epilogue
+    // (~10 k-blocks' worth at 256 streams) plus its K slice, and the grid runs in as many waves as the SMs -- or, for
+    // clusters, the GPCs (16-20 SMs each: cudaOccupancyMaxActiveClusters) -- can hold at once.
     const int kb = K / TC_BK;
-    const long long base = (long long)n_tiles * ceil_div(M, g.bmx);
-    double best = 0.0;
+    const long long tiles = (long long)n_tiles * ceil_div(M, g.bmx);
+    double best = 1e30;
     for (int s = 1; s <= env_split; ++s) {
       const int per = ceil_div(kb, s);
       if (per < 4 && s > 1) break;
       const int s_eff = ceil_div(kb, per);
-      const long long ctas = base * s_eff;
-      const double eff = (double)ctas / (double)(ceil_div(ctas, 148LL) * 148);
-      if (eff > best + 0.02) best = eff, g.split_k = s_eff;
+      if (s_eff != s) continue;
+      const long long per_wave = s == 1 ? 148 : tc_cluster_capacity(g.bmx, mode, s);
+      if (per_wave <= 0) continue;
+      const double cost = (double)ceil_div(tiles, per_wave) * (10.0 + per);
+      if (cost < best * 0.98) best = cost, g.split_k = s;
     }
   }
   make_map(&g.map_w, W, (uint64_t)N, (uint64_t)K, TC_BN);

@@ -9,7 +9,8 @@
 //   warp 2            : TMEM alloc / dealloc
 //   warps 0-3         : epilogue -- tcgen05.ld of the warp's 32 TMEM lanes, fused op, coalesced stores
 // Epilogues: plain f32 store (QKV, text head), residual accumulate x += acc (out-proj, MLP-out; with
-// split-K the partial sums are combined by f32 atomics on x), and the gated-MLP pair
+// split-K the CTAs of a tile form a thread-block cluster and add their partial tiles through distributed shared
+// memory in rank order, so results are bit-reproducible from run to run), and the gated-MLP pair
 // silu(gate) * value -> bf16, where the CTA accumulates gate rows [j0, j0+128) and value rows
 // [hidden + j0, ...) side by side in TMEM (batched_transformer.rs:170-176).
 #pragma once

@@ -731,11 +731,8 @@ template <int BN, bool PRE>
 static void launch6(const Tc6Gemm& g, cudaStream_t st) {
   using C = T6Cfg<BN, PRE>;
   auto kern = tc6_gemm_kernel<BN, C::WS, PRE>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr;
+  attr.run([&] { DSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); });
   Tc6Params p;
   p.K = g.K, p.N = g.N, p.T_out = g.T_out, p.B = g.B, p.t_sub = g.t_sub, p.b_sub = g.b_sub;
   p.t_tiles = ceil_div(g.T_out, g.t_sub), p.nj = g.nj, p.pm = g.pm;

@@ -17,6 +17,34 @@ struct RingState {
 };
 void launch_ring_advance(const RingState& rs, const uint8_t* mask, int B, int t, int context, cudaStream_t st);
 
+// The visibility rules every attention kernel (and the known-answer debug entry dsm_debug_ring_trace) shares.  The
+// reference materialises an additive mask [B, 1, t, ctx]; here it is recomputed from (write index, position).
+#ifdef __CUDACC__
+// slot the s-th new token of this step is written to (kv_cache.rs:216-223)
+__device__ __forceinline__ int ring_write_slot(int i0, int s, int context) {
+  const int w = i0 + s;
+  return w >= context ? w - context : w;
+}
+// t == 1 fast path (kv_cache.rs:130-170: slot j is masked iff j > position): visible slots are [0, n)
+__device__ __forceinline__ int ring_visible_count(uint32_t p0, int context) {
+  return p0 + 1 < (uint32_t)context ? (int)(p0 + 1) : context;
+}
+// any t (kv_cache.rs:192-229): slot j holds the position the ring layout implies, overridden for the slots written
+// this step; query s (position p0 + s) sees it iff that position <= its own.  An inactive stream's mask is all zero.
+__device__ __forceinline__ bool ring_slot_visible(int j, int i0, long long p0, int t, int context, bool active, int s) {
+  if (!active) return true;
+  long long pj;
+  if (p0 < context) pj = j < p0 ? j : (1LL << 40);
+  else pj = j < i0 ? j + (p0 - i0) : j + (p0 - i0) - context;
+  for (int w = 0; w < t; ++w)
+    if (j == ring_write_slot(i0, w, context)) pj = p0 + w;
+  return pj <= p0 + s;
+}
+#endif
+// Debug: indices [B, t] and the additive mask [B, t, context] (0 / -inf) of the step ring_advance just published.
+void launch_ring_debug(const RingState& rs, const uint8_t* mask, int B, int t, int context, uint32_t* indices, float* amask,
+                       cudaStream_t st);
+
 // ---- SEANet ------------------------------------------------------------------------------------
 // First encoder conv (C_in = 1): x(t) = t < S ? state[b, t] : pcm[b, t - S]; writes raw and ELU copies.
 void launch_init_conv(const float* pcm, const float* state, int S, const float* w /*[C,k]*/, const float* bias,
@@ -80,6 +108,20 @@ void launch_rope_scatter_bf16(const float* qkv, const RingState& rs, int B, int 
 void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint8_t* mask, int B, int H, int D,
                          int context, const __nv_bfloat16* k_ring, const __nv_bfloat16* v_ring,
                          __nv_bfloat16* out, cudaStream_t st);
+// 8-bit ring of one layer (see lm_kernels.cu): K int8 [B,H,ctx,D], V int8 [B,H,ctxp/4,D,4], scales f32 [B,H,ctxp].
+// DSM_KV_INT8K keeps V in bf16 [B,H,ctx,D] (v_bf16 set; v and v_scale unused).
+struct KvRingQ8 {
+  int8_t* k;
+  int8_t* v;
+  float* k_scale;
+  float* v_scale;
+  __nv_bfloat16* v_bf16;
+  int ctxp;   // context rounded up to a multiple of 4
+};
+void launch_rope_scatter_q8(const float* qkv, const RingState& rs, int B, int H, int D, int context, const float* inv_freq,
+                            __nv_bfloat16* q_out, const KvRingQ8& ring, cudaStream_t st);
+void launch_lm_attention_q8(const __nv_bfloat16* q, const RingState& rs, const uint8_t* mask, int B, int H, int D, int context,
+                            const KvRingQ8& ring, __nv_bfloat16* out, cudaStream_t st);
 // h f32 [B, 2*Hd] -> g bf16 [B, Hd] = silu(h[:, :Hd]) * h[:, Hd:]   (batched_transformer.rs:170-176)
 void launch_silu_gate(const float* h, int B, int Hd, __nv_bfloat16* g, cudaStream_t st);
 // greedy sampling (asr.rs:208-210): first argmax over logits [B, V]

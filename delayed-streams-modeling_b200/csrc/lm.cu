@@ -28,8 +28,12 @@ static uint64_t name_seed(const std::string& s) {
   return h;
 }
 
-LmImpl::LmImpl(const dsm_lm_spec& sp, const dsm_weights* w, int dev, int batch) : spec(sp), B(batch), device(dev) {
+LmImpl::LmImpl(const dsm_lm_spec& sp, const dsm_weights* w, int dev, int batch, const dsm_lm_options* opt)
+    : spec(sp), B(batch), device(dev) {
   DSM_CHECK(batch > 0, DSM_ERR_INVALID_ARG, "batch_size must be positive");
+  if (opt) kv_dtype = opt->kv_dtype;
+  DSM_CHECK(kv_dtype == DSM_KV_BF16 || kv_dtype == DSM_KV_INT8 || kv_dtype == DSM_KV_INT8K, DSM_ERR_INVALID_ARG,
+            "unknown kv_dtype %d", kv_dtype);
   D = sp.d_model, H = sp.num_heads, L = sp.num_layers, ctx = sp.context;
   DSM_CHECK(D > 0 && H > 0 && D % H == 0, DSM_ERR_INVALID_ARG, "d_model %d not divisible by num_heads %d", D, H);
   hd = D / H;
@@ -105,9 +109,27 @@ LmImpl::LmImpl(const dsm_lm_spec& sp, const dsm_weights* w, int dev, int batch) 
     y.lin_in = bf16_mat(p + ".gating.linear_in.weight", (size_t)2 * hidden * D, sd);
     y.lin_out = bf16_mat(p + ".gating.linear_out.weight", (size_t)D * hidden, 0.5f / sqrtf((float)hidden));
     const size_t ring_elems = (size_t)B * H * ctx * hd;
-    y.k_ring = arena.alloc<__nv_bfloat16>(ring_elems);
-    y.v_ring = arena.alloc<__nv_bfloat16>(ring_elems);
-    kv_bytes += 2 * ring_elems * 2;
+    y.k_ring = y.v_ring = nullptr;
+    y.q8 = KvRingQ8{};
+    if (kv_dtype != DSM_KV_BF16) {
+      const int ctxp = (ctx + 3) & ~3;
+      y.q8.ctxp = ctxp;
+      y.q8.k = arena.alloc<int8_t>(ring_elems);
+      y.q8.k_scale = arena.alloc<float>((size_t)B * H * ctxp);
+      kv_bytes += ring_elems + (size_t)B * H * ctxp * 4;
+      if (kv_dtype == DSM_KV_INT8) {
+        y.q8.v = arena.alloc<int8_t>((size_t)B * H * ctxp * hd);
+        y.q8.v_scale = arena.alloc<float>((size_t)B * H * ctxp);
+        kv_bytes += (size_t)B * H * ctxp * (hd + 4);
+      } else {
+        y.q8.v_bf16 = arena.alloc<__nv_bfloat16>(ring_elems);
+        kv_bytes += ring_elems * 2;
+      }
+    } else {
+      y.k_ring = arena.alloc<__nv_bfloat16>(ring_elems);
+      y.v_ring = arena.alloc<__nv_bfloat16>(ring_elems);
+      kv_bytes += 2 * ring_elems * 2;
+    }
   }
   out_norm = f32_vec("out_norm.alpha", D);
   text_linear = bf16_mat("text_linear.weight", (size_t)sp.text_out_vocab_size * D, 2.f * sd);
@@ -193,10 +215,17 @@ void LmImpl::build_plan(Plan& p, bool with_cond) {
         g.out_raw = s->qkv, g.o_map = dense_rows(1, 3 * D);
         launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(g, st);
       }
-      launch_rope_scatter_bf16(s->qkv, s->ring, B, s->H, s->hd, s->ctx, s->inv_freq, s->q, y.k_ring, y.v_ring, st);
-      s->profile_begin(st);
-      launch_lm_attention(s->q, s->ring, s->d_mask, B, s->H, s->hd, s->ctx, y.k_ring, y.v_ring, s->attn, st);
-      s->profile_end(st);
+      if (s->kv_dtype != DSM_KV_BF16) {
+        launch_rope_scatter_q8(s->qkv, s->ring, B, s->H, s->hd, s->ctx, s->inv_freq, s->q, y.q8, st);
+        s->profile_begin(st);
+        launch_lm_attention_q8(s->q, s->ring, s->d_mask, B, s->H, s->hd, s->ctx, y.q8, s->attn, st);
+        s->profile_end(st);
+      } else {
+        launch_rope_scatter_bf16(s->qkv, s->ring, B, s->H, s->hd, s->ctx, s->inv_freq, s->q, y.k_ring, y.v_ring, st);
+        s->profile_begin(st);
+        launch_lm_attention(s->q, s->ring, s->d_mask, B, s->H, s->hd, s->ctx, y.k_ring, y.v_ring, s->attn, st);
+        s->profile_end(st);
+      }
       if (s->use_tc) {
         tc_gemm_launch(y.g_out, st);       // x += out_proj(attn)
       } else {

@@ -30,7 +30,8 @@ struct LmImpl {
   struct Layer {
     __nv_bfloat16 *in_proj, *out_proj, *lin_in, *lin_out;
     float *norm1, *norm2;
-    __nv_bfloat16 *k_ring, *v_ring;     // [B, H, ctx, hd]
+    __nv_bfloat16 *k_ring, *v_ring;     // [B, H, ctx, hd]   (kv_dtype == DSM_KV_BF16)
+    KvRingQ8 q8;                        // int8 rings + scales  (kv_dtype == DSM_KV_INT8)
     TcGemm g_qkv, g_out, g_in, g_down;  // tcgen05 GEMM descriptors (tensor maps over the buffers below)
   };
   TcGemm g_text;
@@ -69,7 +70,8 @@ struct LmImpl {
   Plan plan_cond;   // forward with Condition::AddToInput
   GraphExec graph, graph_cond;
 
-  LmImpl(const dsm_lm_spec& spec, const dsm_weights* w, int device, int batch);
+  int kv_dtype = DSM_KV_BF16;
+  LmImpl(const dsm_lm_spec& spec, const dsm_weights* w, int device, int batch, const dsm_lm_options* opt = nullptr);
   ~LmImpl();
   void upload_mask(const uint8_t* host_mask, cudaStream_t st);
   void forward(const uint32_t* text_ids, const uint32_t* audio_ids, const float* cond, const uint8_t* mask,

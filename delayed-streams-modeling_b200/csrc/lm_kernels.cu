@@ -195,8 +195,7 @@ __global__ void __launch_bounds__(128 * GROUPS, GROUPS == 1 ? 8 : 3) lm_attentio
     for (int d = tid; d < D; d += 128) orow[d] = __float2bfloat16_rn(0.f);
     continue;
   }
-  const uint32_t p0 = rs.cur_pos[b];
-  const int n = p0 + 1 < (uint32_t)context ? (int)(p0 + 1) : context;   // visible slots are [0, n)
+  const int n = ring_visible_count(rs.cur_pos[b], context);             // visible slots are [0, n)
   const int c8 = lane % LPK, sub = lane / LPK;
   const float scale = rsqrtf((float)D);
 
@@ -338,6 +337,332 @@ void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint
   else
     fail(DSM_ERR_UNSUPPORTED, "lm_attention: head_dim %d (64 or 128)", D);
   check_launch("lm_attention");
+}
+
+// ================================================================================================
+// 8-bit KV ring (opt-in, dsm_lm_options.kv_dtype = DSM_KV_INT8).  The attention above already runs at the
+// HBM copy rate, so only fewer bytes make it faster -- and a bf16 ring (98.3 MB per stt-1b stream) caps a 180 GB
+// GPU at ~1,700 streams.  Storage per (stream, head):
+//   K  int8 [ctx][D]            one key row = D contiguous bytes, scale k_scale[slot] = absmax / 127
+//   V  int8 [ctxp/4][D][4]      key-quad interleaved: the 4 bytes of a 32-bit word are the SAME channel d of 4
+//                               consecutive slots, scale v_scale[slot]                  (ctxp = ctx rounded up to 4)
+// so that both contractions are integer dot products (IDP4A) with the per-slot scales applied to scalars:
+//   score_j = kscale_j * qscale * sum_d q8[d] * k8[j][d]          (the reduction over d runs inside a K word)
+//   out[d]  = pscale   * sum_j p8[j] * v8[j][d],  p8 = quantised (softmax_j * vscale_j)   (over j inside a V word)
+// The query and the probabilities are split into two int8 terms (x ~ s * (x1 + x2 / 254), 15 bits), so the only
+// rounding that matters is the ring's own 8 bits.
+// ================================================================================================
+__global__ void __launch_bounds__(256) rope_scatter_q8_kernel(const float* __restrict__ qkv, RingState rs, int H, int D,
+                                                               int context, int ctxp, const float* __restrict__ inv_freq,
+                                                               __nv_bfloat16* __restrict__ q_out, int8_t* __restrict__ k_ring,
+                                                               int8_t* __restrict__ v_ring, float* __restrict__ k_scale,
+                                                               float* __restrict__ v_scale,
+                                                               __nv_bfloat16* __restrict__ v_ring_bf16) {
+  const int b = blockIdx.x, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int slot = (int)rs.cur_index[b];
+  const float pos = (float)rs.rope_pos[b];
+  const int HD = H * D, half = D / 2;
+  const float* row = qkv + (long long)b * 3 * HD;
+  for (int h = warp; h < H; h += blockDim.x / 32) {
+    // a lane owns the pairs p = lane, lane + 32 (D = 128) or p = lane (D = 64)
+    float kr[4], vr[4];
+    float kmax = 0.f, vmax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int p = lane + 32 * i;
+      kr[2 * i] = kr[2 * i + 1] = vr[2 * i] = vr[2 * i + 1] = 0.f;
+      if (p >= half) continue;
+      float sn, cs;
+      sincosf(pos * inv_freq[p], &sn, &cs);
+      const float2 q = *reinterpret_cast<const float2*>(row + h * D + 2 * p);
+      const float2 k = *reinterpret_cast<const float2*>(row + HD + h * D + 2 * p);
+      const float2 v = *reinterpret_cast<const float2*>(row + 2 * HD + h * D + 2 * p);
+      *reinterpret_cast<__nv_bfloat162*>(q_out + (long long)b * HD + h * D + 2 * p) =
+          __floats2bfloat162_rn(q.x * cs - q.y * sn, q.x * sn + q.y * cs);
+      kr[2 * i] = k.x * cs - k.y * sn, kr[2 * i + 1] = k.x * sn + k.y * cs;
+      vr[2 * i] = v.x, vr[2 * i + 1] = v.y;
+      kmax = fmaxf(kmax, fmaxf(fabsf(kr[2 * i]), fabsf(kr[2 * i + 1])));
+      vmax = fmaxf(vmax, fmaxf(fabsf(v.x), fabsf(v.y)));
+    }
+    kmax = warp_max(kmax), vmax = warp_max(vmax);
+    const float kinv = kmax > 0.f ? 127.f / kmax : 0.f, vinv = vmax > 0.f ? 127.f / vmax : 0.f;
+    const long long bh = (long long)b * H + h;
+    if (lane == 0) {
+      k_scale[bh * ctxp + slot] = kmax / 127.f;
+      if (!v_ring_bf16) v_scale[bh * ctxp + slot] = vmax / 127.f;
+    }
+    int8_t* kdst = k_ring + (bh * context + slot) * D;
+    int8_t* vdst = v_ring_bf16 ? nullptr : v_ring + bh * ctxp * D + (long long)(slot >> 2) * D * 4 + (slot & 3);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int p = lane + 32 * i;
+      if (p >= half) continue;
+      const int k0 = __float2int_rn(kr[2 * i] * kinv), k1 = __float2int_rn(kr[2 * i + 1] * kinv);
+      *reinterpret_cast<uint16_t*>(kdst + 2 * p) = (uint16_t)((k0 & 0xff) | ((k1 & 0xff) << 8));
+      if (v_ring_bf16) {
+        *reinterpret_cast<__nv_bfloat162*>(v_ring_bf16 + (bh * context + slot) * D + 2 * p) =
+            __floats2bfloat162_rn(vr[2 * i], vr[2 * i + 1]);
+      } else {
+        vdst[(2 * p) * 4] = (int8_t)__float2int_rn(vr[2 * i] * vinv);
+        vdst[(2 * p + 1) * 4] = (int8_t)__float2int_rn(vr[2 * i + 1] * vinv);
+      }
+    }
+  }
+}
+
+void launch_rope_scatter_q8(const float* qkv, const RingState& rs, int B, int H, int D, int context, const float* inv_freq,
+                            __nv_bfloat16* q_out, const KvRingQ8& r, cudaStream_t st) {
+  DSM_CHECK(D == 64 || D == 128, DSM_ERR_UNSUPPORTED, "rope_scatter_q8: head_dim %d (64 or 128)", D);
+  rope_scatter_q8_kernel<<<B, 256, 0, st>>>(qkv, rs, H, D, context, r.ctxp, inv_freq, q_out, r.k, r.v, r.k_scale, r.v_scale,
+                                            r.v_bf16);
+  check_launch("rope_scatter_q8");
+}
+
+// x -> two int8 terms: x * inv ~ x1 + x2 / 254, |x1| <= 127, |x2| <= 127
+__device__ __forceinline__ void split2_i8(float t, int& x1, int& x2) {
+  const float r = rintf(t);
+  x1 = (int)r;
+  x2 = __float2int_rn((t - r) * 254.f);
+}
+__device__ __forceinline__ uint32_t pack4_i8(int a, int b, int c, int d) {
+  return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+}
+
+// One CTA (4 warps) per (stream, head), as the bf16 kernel.  K pass: a key row is D/16 lanes x 16 B, 32 / (D/16)
+// keys per warp-load.  V pass: a key-quad block is D*4 bytes = D/4 lanes x 16 B; a lane owns 4 channels.
+// V8 = false: the V ring stays bf16 [ctx][D] (DSM_KV_INT8K) and P.V is the bf16 kernel's f32 pass.
+template <int D, int UNROLL, bool V8>
+__global__ void __launch_bounds__(128, 8) lm_attention_q8_kernel(const __nv_bfloat16* __restrict__ q, RingState rs,
+                                                                  const uint8_t* __restrict__ mask, int H, int context,
+                                                                  int ctxp, const int8_t* __restrict__ k_ring,
+                                                                  const int8_t* __restrict__ v_ring,
+                                                                  const float* __restrict__ k_scale,
+                                                                  const float* __restrict__ v_scale,
+                                                                  const __nv_bfloat16* __restrict__ v_ring_bf16,
+                                                                  __nv_bfloat16* __restrict__ out) {
+  constexpr int LPK = D / 16;         // lanes per key row
+  constexpr int KPW = 32 / LPK;       // keys per warp-load
+  constexpr int LPB = D / 4;          // lanes per key-quad block
+  constexpr int BPW = 32 / LPB;       // blocks per warp-load
+  constexpr int NW = 4;
+  extern __shared__ float sm[];
+  float* sc = sm;                                            // [ctxp] scores, then p * vscale
+  uint2* pq = reinterpret_cast<uint2*>(sm + ctxp);           // [ctxp/4] {4 x p1, 4 x p2} per key quad
+  int* red = reinterpret_cast<int*>(sm + ctxp + ctxp / 2);   // [NW][D][2] partial integer outputs
+  __shared__ float s_red[2][NW];
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int HD = H * D;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  __nv_bfloat16* orow = out + (long long)b * HD + h * D;
+  if (mask && !mask[b]) {
+    for (int d = tid; d < D; d += 128) orow[d] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const int n = ring_visible_count(rs.cur_pos[b], context);             // visible slots are [0, n)
+  const int n4 = (n + 3) & ~3;
+  const long long bh = (long long)b * H + h;
+  const float* ks = k_scale + bh * ctxp;
+  const float* vs = v_scale + bh * ctxp;
+
+  // ---- query: bf16 -> two int8 terms with one scale per head ----
+  const int c16 = lane % LPK, sub = lane / LPK;
+  uint32_t q1[4], q2[4];
+  float qs;
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(q + (long long)b * HD + h * D + c16 * 16);
+    const uint4 u0 = qp[0], u1 = qp[1];
+    const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    float qf[16];
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      qf[2 * i] = bf16_lo(w[i]), qf[2 * i + 1] = bf16_hi(w[i]);
+      amax = fmaxf(amax, fmaxf(fabsf(qf[2 * i]), fabsf(qf[2 * i + 1])));
+    }
+#pragma unroll
+    for (int o = LPK / 2; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float inv = amax > 0.f ? 127.f / amax : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int a1[4], a2[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split2_i8(qf[4 * i + e] * inv, a1[e], a2[e]);
+      q1[i] = pack4_i8(a1[0], a1[1], a1[2], a1[3]);
+      q2[i] = pack4_i8(a2[0], a2[1], a2[2], a2[3]);
+    }
+    qs = amax * (1.f / (127.f * 254.f)) * rsqrtf((float)D);
+  }
+  const int8_t* kb = k_ring + bh * context * D;
+  const int8_t* vb = v_ring + bh * ctxp * D;
+
+  // ---- scores (integer dot products; the key's scale is applied in the softmax pass) ----
+  for (int j0 = warp * KPW * UNROLL; j0 < n; j0 += NW * KPW * UNROLL) {
+    uint4 kv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int j = j0 + u * KPW + sub;
+      kv[u] = j < n ? ld_stream16(kb + (long long)j * D + c16 * 16) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      int hi = __dp4a((int)kv[u].x, (int)q1[0], 0), lo = __dp4a((int)kv[u].x, (int)q2[0], 0);
+      hi = __dp4a((int)kv[u].y, (int)q1[1], hi), lo = __dp4a((int)kv[u].y, (int)q2[1], lo);
+      hi = __dp4a((int)kv[u].z, (int)q1[2], hi), lo = __dp4a((int)kv[u].z, (int)q2[2], lo);
+      hi = __dp4a((int)kv[u].w, (int)q1[3], hi), lo = __dp4a((int)kv[u].w, (int)q2[3], lo);
+      int t = hi * 254 + lo;      // |t| <= 16 * 127 * 127 * 255 < 2^26
+#pragma unroll
+      for (int o = LPK / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      const int j = j0 + u * KPW + sub;
+      if (c16 == 0 && j < n) sc[j] = (float)t;
+    }
+  }
+  __syncthreads();
+
+  // ---- softmax (f32); p_j * vscale_j quantised to two int8 terms against its maximum ----
+  float mx = -INFINITY;
+  for (int j = tid; j < n; j += 128) {
+    const float s = sc[j] * (ks[j] * qs);
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_red[0][warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_red[0][0], s_red[0][1]), fmaxf(s_red[0][2], s_red[0][3]));
+  __syncthreads();
+  float sum = 0.f, pm = 0.f;
+  for (int j = tid; j < n; j += 128) {
+    const float e = __expf(sc[j] - mx);
+    const float pv = V8 ? e * vs[j] : e;
+    sc[j] = pv;
+    sum += e;
+    pm = fmaxf(pm, pv);
+  }
+  sum = warp_sum(sum), pm = warp_max(pm);
+  if (lane == 0) s_red[0][warp] = sum, s_red[1][warp] = pm;
+  __syncthreads();
+  sum = s_red[0][0] + s_red[0][1] + s_red[0][2] + s_red[0][3];
+  if (!V8) {
+    // ---- P.V with a bf16 V ring: the bf16 kernel's pass (D/8 lanes x 16 B per key row) ----
+    constexpr int LPK2 = D / 8, KPW2 = 32 / LPK2;
+    const int c8 = lane % LPK2, sub2 = lane / LPK2;
+    const __nv_bfloat16* vbf = v_ring_bf16 + bh * context * D;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int j0 = warp * KPW2 * UNROLL; j0 < n; j0 += NW * KPW2 * UNROLL) {
+      uint4 vv[UNROLL];
+      float pj[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int j = j0 + u * KPW2 + sub2;
+        const bool ok = j < n;
+        vv[u] = ok ? ld_stream16(vbf + (long long)j * D + c8 * 8) : make_uint4(0, 0, 0, 0);
+        pj[u] = ok ? sc[j] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        acc[0] = fmaf(pj[u], bf16_lo(vv[u].x), acc[0]);
+        acc[1] = fmaf(pj[u], bf16_hi(vv[u].x), acc[1]);
+        acc[2] = fmaf(pj[u], bf16_lo(vv[u].y), acc[2]);
+        acc[3] = fmaf(pj[u], bf16_hi(vv[u].y), acc[3]);
+        acc[4] = fmaf(pj[u], bf16_lo(vv[u].z), acc[4]);
+        acc[5] = fmaf(pj[u], bf16_hi(vv[u].z), acc[5]);
+        acc[6] = fmaf(pj[u], bf16_lo(vv[u].w), acc[6]);
+        acc[7] = fmaf(pj[u], bf16_hi(vv[u].w), acc[7]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int o = LPK2; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    __syncthreads();                    // every warp is done reading the probabilities in sc[]
+    float* redf = sc;                   // [NW][D], ctxp >= 4 * D is not guaranteed: use the integer scratch when short
+    if (ctxp < NW * D) redf = reinterpret_cast<float*>(red);
+    if (sub2 == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) redf[warp * D + c8 * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    const float inv = 1.f / sum;
+    for (int d = tid; d < D; d += 128) orow[d] = __float2bfloat16_rn((redf[d] + redf[D + d] + redf[2 * D + d] + redf[3 * D + d]) * inv);
+    return;
+  }
+  pm = fmaxf(fmaxf(s_red[1][0], s_red[1][1]), fmaxf(s_red[1][2], s_red[1][3]));
+  const float pinv = pm > 0.f ? 127.f / pm : 0.f;
+  int8_t* pq8 = reinterpret_cast<int8_t*>(pq);
+  for (int j = tid; j < n4; j += 128) {
+    int p1 = 0, p2 = 0;
+    if (j < n) split2_i8(sc[j] * pinv, p1, p2);
+    pq8[(j >> 2) * 8 + (j & 3)] = (int8_t)p1;
+    pq8[(j >> 2) * 8 + 4 + (j & 3)] = (int8_t)p2;
+  }
+  __syncthreads();
+
+  // ---- P.V: per lane 4 channels x {hi, lo} integer accumulators ----
+  const int nb = n4 >> 2;
+  const int lb = lane % LPB, bsub = lane / LPB;
+  int ah[4] = {0, 0, 0, 0}, al[4] = {0, 0, 0, 0};
+  for (int kb0 = warp * BPW * UNROLL; kb0 < nb; kb0 += NW * BPW * UNROLL) {
+    uint4 vv[UNROLL];
+    uint2 pp[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int kq = kb0 + u * BPW + bsub;
+      const bool ok = kq < nb;
+      vv[u] = ok ? ld_stream16(vb + (long long)kq * D * 4 + lb * 16) : make_uint4(0, 0, 0, 0);
+      pp[u] = ok ? pq[kq] : make_uint2(0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      ah[0] = __dp4a((int)vv[u].x, (int)pp[u].x, ah[0]), al[0] = __dp4a((int)vv[u].x, (int)pp[u].y, al[0]);
+      ah[1] = __dp4a((int)vv[u].y, (int)pp[u].x, ah[1]), al[1] = __dp4a((int)vv[u].y, (int)pp[u].y, al[1]);
+      ah[2] = __dp4a((int)vv[u].z, (int)pp[u].x, ah[2]), al[2] = __dp4a((int)vv[u].z, (int)pp[u].y, al[2]);
+      ah[3] = __dp4a((int)vv[u].w, (int)pp[u].x, ah[3]), al[3] = __dp4a((int)vv[u].w, (int)pp[u].y, al[3]);
+    }
+  }
+  // fold the BPW block sub-groups of a warp (D = 64), then the warps
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int o = LPB; o < 32; o <<= 1) {
+      ah[i] += __shfl_xor_sync(0xffffffffu, ah[i], o);
+      al[i] += __shfl_xor_sync(0xffffffffu, al[i], o);
+    }
+  }
+  if (bsub == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      red[(warp * D + lb * 4 + i) * 2] = ah[i];
+      red[(warp * D + lb * 4 + i) * 2 + 1] = al[i];
+    }
+  }
+  __syncthreads();
+  const float oscale = pm * (1.f / 127.f) / sum;
+  for (int d = tid; d < D; d += 128) {
+    int hi = 0, lo = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) hi += red[(w * D + d) * 2], lo += red[(w * D + d) * 2 + 1];
+    orow[d] = __float2bfloat16_rn(((float)hi + (float)lo * (1.f / 254.f)) * oscale);
+  }
+}
+
+size_t lm_attention_q8_smem(int D, int ctxp) { return (size_t)(ctxp + ctxp / 2 + 4 * D * 2) * sizeof(float); }
+
+void launch_lm_attention_q8(const __nv_bfloat16* q, const RingState& rs, const uint8_t* mask, int B, int H, int D, int context,
+                            const KvRingQ8& r, __nv_bfloat16* out, cudaStream_t st) {
+  const size_t smem = lm_attention_q8_smem(D, r.ctxp);
+  DSM_CHECK(smem <= 48 * 1024, DSM_ERR_UNSUPPORTED, "lm_attention_q8: context %d needs %zu bytes of shared memory", context, smem);
+#define Q8_ARGS q, rs, mask, H, context, r.ctxp, r.k, r.v, r.k_scale, r.v_scale, r.v_bf16, out
+  if (D == 128 && !r.v_bf16) lm_attention_q8_kernel<128, 8, true><<<B * H, 128, smem, st>>>(Q8_ARGS);
+  else if (D == 128) lm_attention_q8_kernel<128, 8, false><<<B * H, 128, smem, st>>>(Q8_ARGS);
+  else if (D == 64 && !r.v_bf16) lm_attention_q8_kernel<64, 8, true><<<B * H, 128, smem, st>>>(Q8_ARGS);
+  else if (D == 64) lm_attention_q8_kernel<64, 8, false><<<B * H, 128, smem, st>>>(Q8_ARGS);
+#undef Q8_ARGS
+  else
+    fail(DSM_ERR_UNSUPPORTED, "lm_attention_q8: head_dim %d (64 or 128)", D);
+  check_launch("lm_attention_q8");
 }
 
 // ================================================================================================

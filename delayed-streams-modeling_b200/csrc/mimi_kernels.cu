@@ -30,6 +30,30 @@ void launch_ring_advance(const RingState& rs, const uint8_t* mask, int B, int t,
   check_launch("ring_advance");
 }
 
+// What the attention kernels see, written out (known-answer check against kv_cache.rs:338-405).  t == 1 uses the
+// LM kernels' fast-path rule, t > 1 the general one of the codec kernel.
+__global__ void ring_debug_kernel(RingState rs, const uint8_t* __restrict__ mask, int t, int context,
+                                  uint32_t* __restrict__ indices, float* __restrict__ amask) {
+  const int b = blockIdx.x;
+  const bool active = mask ? mask[b] != 0 : true;
+  const int i0 = (int)rs.cur_index[b];
+  const uint32_t p0 = rs.cur_pos[b];
+  for (int s = threadIdx.x; s < t; s += blockDim.x)
+    indices[b * t + s] = active ? (uint32_t)ring_write_slot(i0, s, context) : (uint32_t)i0;
+  for (int i = threadIdx.x; i < t * context; i += blockDim.x) {
+    const int s = i / context, j = i - s * context;
+    bool vis;
+    if (t == 1) vis = !active || j < ring_visible_count(p0, context);
+    else vis = ring_slot_visible(j, i0, (long long)p0, t, context, active, s);
+    amask[((long long)b * t + s) * context + j] = vis ? 0.f : -INFINITY;
+  }
+}
+void launch_ring_debug(const RingState& rs, const uint8_t* mask, int B, int t, int context, uint32_t* indices, float* amask,
+                       cudaStream_t st) {
+  ring_debug_kernel<<<B, 128, 0, st>>>(rs, mask, t, context, indices, amask);
+  check_launch("ring_debug");
+}
+
 // ================================================================================================
 // SEANet first conv: C_in = 1, k taps, stride 1 (seanet.rs:177-190).  HBM-bound on its output
 // ([B, T, C] f32 written twice: raw for the residual path, ELU'd for the next conv).
@@ -374,19 +398,7 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
   // overridden for the slots written this step.
   if (warp < t) {
     float* row = sc + warp * context;
-    const long long off = p0 - i0;
-    auto visible = [&](int j) -> bool {
-      if (!active) return true;
-      long long pj;
-      if (p0 < context) pj = j < p0 ? j : (1LL << 40);
-      else pj = j < i0 ? j + off : j + off - context;
-      for (int s = 0; s < t; ++s) {
-        int ws = i0 + s;
-        if (ws >= context) ws -= context;
-        if (j == ws) pj = p0 + s;
-      }
-      return pj <= p0 + warp;
-    };
+    auto visible = [&](int j) -> bool { return ring_slot_visible(j, i0, p0, t, context, active, warp); };
     float mx = -INFINITY;
     for (int j = lane; j < context; j += 32) {
       const float x = visible(j) ? row[j] : -INFINITY;

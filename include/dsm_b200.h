@@ -129,6 +129,14 @@ dsm_status dsm_debug_gemm_bf16(int32_t impl, int32_t mode, int32_t M, int32_t N,
 dsm_status dsm_debug_gemm_f32(int32_t impl, int32_t B, int32_t T, int64_t stride_b, int64_t stride_t, int32_t N, int32_t K,
                               const float* A, int64_t a_elems, const float* W, const float* bias, float* out);
 
+/* Known-answer access to the DEVICE ring bookkeeping (ScatteredCacheBuilder::indices_and_mask, kv_cache.rs:119-237,
+ * test table :338-405): a fresh ring of `batch` streams and `context` slots is stepped n_steps times on device 0; step i
+ * appends t[i] tokens under masks[i*batch .. ] (1 = active).  Outputs, concatenated over the steps: the scatter indices
+ * [batch, t[i]] u32 and the additive mask [batch, t[i], context] f32 (0 / -inf) exactly as the attention kernels
+ * reconstruct visibility (the same device functions). */
+dsm_status dsm_debug_ring_trace(int32_t batch, int32_t context, int32_t n_steps, const int32_t* t, const uint8_t* masks,
+                                uint32_t* indices_out, float* mask_out);
+
 void dsm_mimi_spec_v0_1(dsm_mimi_spec* spec, int32_t n_q);            /* mimi.rs:32 Config::v0_1 */
 void dsm_lm_spec_stt_1b_en_fr(dsm_lm_spec* spec);                     /* config-stt-en_fr-hf.toml */
 void dsm_lm_spec_stt_2_6b_en(dsm_lm_spec* spec);                      /* config-stt-en-hf.toml */
@@ -168,6 +176,20 @@ int64_t dsm_mimi_kv_bytes(const dsm_mimi* h);
  * (model_dtype == bf16 on CUDA, moshi-server/src/utils.rs:386-395). */
 dsm_status dsm_lm_create(const dsm_lm_spec* spec, const dsm_weights* weights, int32_t device,
                          int32_t batch_size, dsm_lm** out);
+/* Storage format of the LM's ring KV cache (kv_cache.rs:20-51 keeps it in the model dtype = bf16, the default here).
+ * DSM_KV_INT8 halves the ring (98.3 -> 50.8 MB per stt-1b stream, the route past ~1,700 streams per 180 GB GPU):
+ * int8 K / V with one f32 scale per (stream, head, slot), dequantised inside the attention kernel.  It is an
+ * approximation of the reference (measured logits error in DESIGN.md section 4), hence opt-in.
+ * DSM_KV_INT8K keeps V in bf16 and only K in int8 (74.5 MB per stream): three quarters of the bytes, half the error. */
+enum { DSM_KV_BF16 = 0, DSM_KV_INT8 = 1, DSM_KV_INT8K = 2 };
+typedef struct dsm_lm_options {
+  int32_t kv_dtype;     /* DSM_KV_* */
+  int32_t reserved[7];  /* zero */
+} dsm_lm_options;
+/* dsm_lm_create with options (NULL = defaults = dsm_lm_create). */
+dsm_status dsm_lm_create_ex(const dsm_lm_spec* spec, const dsm_weights* weights, int32_t device, int32_t batch_size,
+                            const dsm_lm_options* options, dsm_lm** out);
+int32_t dsm_lm_kv_dtype(const dsm_lm* h);
 void dsm_lm_destroy(dsm_lm* h);
 /* LmModel::forward_cond (lm.rs:957-1008): text_ids [B] u32, audio_ids [B,n_cb] u32,
  * cond [d_model] f32 or NULL (Condition::AddToInput) -> logits [B,V] f32 and ys [B,D] f32 (either

@@ -1,6 +1,9 @@
-"""Size-independent properties at BASELINE.json's full size (stt-1b-en_fr, 256 streams, random init):
-determinism, stream independence (permuting the batch permutes the outputs), masked streams leave no
-trace.  No oracle involved: the CPU oracle cannot run this size in seconds."""
+"""BASELINE.json's full size (stt-1b-en_fr, 256 streams, random init): size-independent properties --
+determinism, stream independence (permuting the batch permutes the outputs bit for bit), masked streams leave no
+trace -- and a direct comparison with the CPU oracle at 256 streams (short LM ring so the f32 oracle's KV fits in
+host memory; the full 750-slot ring is compared in test_gpu_lm_kv.py)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -43,14 +46,14 @@ def test_permutation_equivariance_and_mask_isolation():
         a2.step_pcm(frame(audio[perm], i))
         c2 = probe2.encode_step(frame(audio[perm], i))
         assert (c2 == codes1[i][perm]).all(), "RVQ codes depend on the position of a stream in the batch"
-        # The LM is not bit-reproducible across batch layouts: split-K partial sums are combined with f32
-        # atomics, and a 1e-7 difference can flip a bf16 rounding that then propagates.  Logits must
-        # agree to bf16 tolerance; greedy tokens of near-uniform random-init logits may flip rarely.
+        # Nothing in the step depends on where a stream sits in the batch: the GEMMs accumulate every output element in
+        # the same K order (split-K partials are added in cluster-rank order, not by atomics), so the logits must agree
+        # to the last bit and every greedy token must match.
         l2 = a2.last_logits()
-        err = np.abs(l2 - logits1[i][perm])[agree].max() / np.abs(l2).max()
-        assert err < 2e-2, f"logits depend on the position of a stream in the batch (rel {err:.3e})"
+        err = np.abs(l2 - logits1[i][perm]).max() / np.abs(l2).max()
+        assert err < 1e-6, f"logits depend on the position of a stream in the batch (rel {err:.3e})"
         agree &= a2.last_tokens == toks1[i][perm]
-    assert agree.mean() >= 0.9, f"greedy tokens diverged on {100 * (1 - agree.mean()):.1f}% of streams"
+    assert agree.all(), f"greedy tokens diverged on {int((~agree).sum())} of {B} streams"
 
 
 def test_masked_streams_do_not_advance():
@@ -67,5 +70,47 @@ def test_masked_streams_do_not_advance():
     ref.step_pcm(frame(audio, 2))
     odd = np.arange(B)[1::2]
     err = np.abs(a.last_logits()[odd] - ref.last_logits()[odd]).max() / np.abs(ref.last_logits()).max()
-    assert err < 2e-2
-    assert (a.last_tokens[odd] == ref.last_tokens[odd]).mean() >= 0.95
+    assert err < 1e-6
+    assert (a.last_tokens[odd] == ref.last_tokens[odd]).all()
+
+
+def test_oracle_comparison_at_256_streams():
+    """Mimi v0_1 + the 16-layer stt-1b LM at 256 streams against the CPU oracle for 3 frames (one of them masked):
+    RVQ codes bit-identical on >= 99.5 % of the active stream-frames, logits within rel 1e-2, greedy tokens equal."""
+    import torch
+    from dsm_b200 import api
+    from dsm_b200.spec import LmSpec, MimiSpec
+    from dsm_b200.weights import lm_weights, mimi_weights
+    from helpers import oracle_lm_weights, rel_err
+    from oracle.lm import AsrState as OAsr, LmModel as OLm
+    from oracle.mimi import Mimi as OMimi
+    torch.set_num_threads(os.cpu_count() or 8)
+    mspec, lspec = MimiSpec(), LmSpec(context=16)       # f32 oracle KV at ring 750 would need 100 GB of host memory
+    mw = mimi_weights(mspec, seed=0, layer_scale=0.5, decoder=False)
+    lw = lm_weights(lspec, seed=0)
+    g_mimi, g_lm = api.Mimi(mspec, mw, B, decoder=False), api.LmModel(lspec, lw, B)
+    g = api.AsrState(g_mimi, g_lm)
+    probe = api.Mimi(mspec, mw, B, decoder=False)
+    o = OAsr(B, lspec.asr_delay_in_tokens, OMimi(mspec, mw, B, decoder=False), OLm(lspec, oracle_lm_weights(lw), B))
+    del lw
+    o_probe = OMimi(mspec, mw, B, decoder=False)
+    audio = synth_audio(B, 3)
+    rng = np.random.default_rng(1)
+    same = total = 0
+    for i in range(3):
+        mask = None if i != 1 else (rng.random(B) > 0.25).astype(np.uint8)
+        act = np.ones(B, bool) if mask is None else mask.astype(bool)
+        fr = frame(audio, i)
+        gc = probe.encode_step(fr, mask)
+        oc = o_probe.encode_step(torch.from_numpy(fr).unsqueeze(1), None if mask is None else act)[:, :, 0].numpy()
+        same += int((gc.astype(np.int64)[act] == oc[act]).all(axis=1).sum())
+        total += int(act.sum())
+        g.step_pcm(fr, mask)
+        # random-init logits over 8000 entries are nearly flat: where the device's token is a near-tie of the oracle's
+        # argmax (gap inside the logits tolerance) the oracle follows it so later frames stay comparable
+        o.follow_tokens, o.tie_tol = g.last_tokens.astype(np.int64), 1e-2
+        o.step_pcm(torch.from_numpy(fr).unsqueeze(1), None if mask is None else act)
+        assert rel_err(g.last_logits()[act], o.last_logits.numpy()[act]) < 1e-2
+        assert (g.last_tokens[act] == o.last_tokens.numpy()[act]).all(), f"frame {i}: greedy tokens differ"
+    assert same >= 0.995 * total, f"RVQ codes identical on {same}/{total} stream-frames"
+    assert o.ties_followed <= 0.01 * total, f"{o.ties_followed} near-tie flips in {total} stream-frames"
