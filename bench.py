@@ -233,8 +233,9 @@ def run_reference(args):
     cfg["streams_per_gpu"] = streams
     cfg["cpu_lm_context"] = CPU_LM_CONTEXT
     cfg.pop("ring_prefill_steps", None)
-    sample = (f"{streams} streams x {steps} steps of the {args.workload} workload, LM ring {CPU_LM_CONTEXT} slots (the f32 "
-              f"750-slot KV of {streams} streams would not fit in host memory); oracle = PyTorch CPU f32 restatement of the "
+    cfg.pop("lm_kv", None)
+    sample = (f"{streams} streams x {steps} steps of the {args.workload} workload, LM ring {CPU_LM_CONTEXT} slots (an f32 "
+              "750-slot KV is 0.39 GB per stream of host memory); oracle = PyTorch CPU f32 restatement of the "
               "reference's candle CPU path")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
