@@ -57,6 +57,23 @@ class AsrMsgC(C.Structure):
                 ("tokens", C.POINTER(C.c_uint32)), ("time", C.c_double), ("prs", C.POINTER(C.c_float))]
 
 
+class AsrConfigC(C.Structure):
+    _fields_ = [("lm", LmSpecC), ("asr_delay_in_tokens", C.c_int32), ("has_conditioning_delay", C.c_int32),
+                ("conditioning_delay", C.c_float), ("temperature", C.c_float), ("batch_size", C.c_int32),
+                ("module_type", C.c_char * 32), ("lm_model_file", C.c_char * 512), ("audio_tokenizer_file", C.c_char * 512),
+                ("text_tokenizer_file", C.c_char * 512)]
+
+
+class WireInC(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("id", C.c_int64), ("n", C.c_int64), ("pcm", C.POINTER(C.c_float)),
+                ("data", C.POINTER(C.c_uint8))]
+
+
+class WireOutC(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("text", C.c_void_p), ("text_len", C.c_int32), ("time", C.c_double), ("id", C.c_int64),
+                ("step_idx", C.c_int64), ("prs", C.POINTER(C.c_float)), ("n_prs", C.c_int32), ("buffered_pcm", C.c_int64)]
+
+
 class LmOptionsC(C.Structure):
     _fields_ = [("kv_dtype", C.c_int32), ("reserved", C.c_int32 * 7)]
 
@@ -133,6 +150,22 @@ SIGNATURES = {
     "dsm_asr_delay_in_tokens": (C.c_int32, [_P]),
     "dsm_asr_last_logits": (C.c_int32, [_P, _P]),
     "dsm_asr_last_step_ms": (C.c_int32, [_P, C.POINTER(C.c_float * 3)]),
+    "dsm_weights_open": (C.c_int32, [C.c_char_p, C.POINTER(_P)]),
+    "dsm_weight_file_table": (C.POINTER(Weights), [_P]),
+    "dsm_weight_file_metadata": (C.c_int64, [_P, C.c_char_p, C.c_char_p, C.c_size_t]),
+    "dsm_weight_file_close": (None, [_P]),
+    "dsm_weights_save": (C.c_int32, [C.c_char_p, C.POINTER(Weights)]),
+    "dsm_asr_config_from_toml": (C.c_int32, [C.c_char_p, C.c_char_p, C.POINTER(AsrConfigC)]),
+    "dsm_asr_config_from_toml_text": (C.c_int32, [C.c_char_p, C.c_char_p, C.POINTER(AsrConfigC)]),
+    "dsm_wire_encode_out": (C.c_int32, [C.POINTER(WireOutC), _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "dsm_wire_decode_out": (C.c_int32, [_P, C.c_size_t, C.POINTER(WireOutC), _P, C.c_int32]),
+    "dsm_wire_encode_in": (C.c_int32, [C.POINTER(WireInC), _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "dsm_wire_decode_in": (C.c_int32, [_P, C.c_size_t, C.POINTER(WireInC), _P, C.c_int64, _P, C.c_int64]),
+    "dsm_spm_open": (C.c_int32, [C.c_char_p, C.POINTER(_P)]),
+    "dsm_spm_close": (None, [_P]),
+    "dsm_spm_vocab_size": (C.c_int32, [_P]),
+    "dsm_spm_piece": (C.c_char_p, [_P, C.c_int32]),
+    "dsm_spm_decode": (C.c_int32, [_P, _P, C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dsm_sched_create": (C.c_int32, [_P, C.c_int32, C.POINTER(_P)]),
     "dsm_sched_destroy": (None, [_P]),
     "dsm_sched_open": (C.c_int32, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),

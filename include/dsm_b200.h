@@ -297,6 +297,80 @@ int64_t dsm_sched_step_idx(const dsm_sched* h);
 const uint8_t* dsm_sched_last_mask(const dsm_sched* h);
 const float* dsm_sched_batch_pcm(const dsm_sched* h);
 
+/* ---- weight and configuration files (host side; moshi-server/src/batched_asr.rs:738-771) -------------------- */
+/* A safetensors file mapped read-only: what candle's VarBuilder::from_mmaped_safetensors hands the reference's
+ * constructors.  The table points INTO the mapping: keep the file open until the create call that consumes it has
+ * returned (create copies to the device).  F32 / BF16 / F16 tensors; the load-time folds (weight-norm conv.rs:27-45,
+ * codebooks quantization.rs:86-107) happen inside dsm_mimi_create. */
+typedef struct dsm_weight_file dsm_weight_file;
+dsm_status dsm_weights_open(const char* safetensors_path, dsm_weight_file** out);
+const dsm_weights* dsm_weight_file_table(const dsm_weight_file* f);
+/* __metadata__ entry `key` copied into buf; returns its length or -1 when absent. */
+int64_t dsm_weight_file_metadata(const dsm_weight_file* f, const char* key, char* buf, size_t cap);
+void dsm_weight_file_close(dsm_weight_file* f);
+/* Writes a table as a safetensors file (tests, checkpoint conversion tooling). */
+dsm_status dsm_weights_save(const char* safetensors_path, const dsm_weights* weights);
+
+/* The reference's server TOML (configs/stt/config-stt-*.toml): [modules.<module>] + .model + .model.transformer +
+ * .model.extra_heads -> the LM spec and the AsrConfig fields beside it.  Keys this library does not implement with
+ * another value than the STT configs use (gating, norm, positional_embedding, kv_repeat, ...) are refused. */
+typedef struct dsm_asr_config {
+  dsm_lm_spec lm;
+  int32_t asr_delay_in_tokens;      /* or conditioning_delay * 12.5 + 1 when that key is present (batched_asr.rs:769-770) */
+  int32_t has_conditioning_delay;
+  float conditioning_delay;
+  float temperature;
+  int32_t batch_size;
+  char module_type[32];             /* "BatchedAsr" / "Asr" */
+  char lm_model_file[512];
+  char audio_tokenizer_file[512];
+  char text_tokenizer_file[512];
+} dsm_asr_config;
+dsm_status dsm_asr_config_from_toml(const char* toml_path, const char* module /* NULL = "asr" */, dsm_asr_config* out);
+dsm_status dsm_asr_config_from_toml_text(const char* toml_text, const char* module, dsm_asr_config* out);
+
+/* ---- wire messages (moshi-server/src/asr.rs:15-34) ------------------------------------------------------------ */
+/* MessagePack bytes exactly as rmp_serde writes InMsg / OutMsg with `.with_struct_map()`: a map whose first entry is
+ * "type" -> variant name, then the fields in declaration order.  Known-answer bytes:
+ * client/rust/kyutai-client/src/stt/protocol.rs:81-96. */
+enum { DSM_WIRE_IN_INIT = 0, DSM_WIRE_IN_MARKER = 1, DSM_WIRE_IN_AUDIO = 2, DSM_WIRE_IN_OGG_OPUS = 3, DSM_WIRE_IN_PING = 4 };
+typedef struct dsm_wire_in {
+  int32_t kind;
+  int64_t id;           /* Marker */
+  int64_t n;            /* Audio: samples; OggOpus: bytes */
+  const float* pcm;     /* Audio */
+  const uint8_t* data;  /* OggOpus (the Ogg/Opus decoder itself is outside this library) */
+} dsm_wire_in;
+enum { DSM_WIRE_OUT_WORD = 0, DSM_WIRE_OUT_END_WORD = 1, DSM_WIRE_OUT_MARKER = 2, DSM_WIRE_OUT_STEP = 3,
+       DSM_WIRE_OUT_ERROR = 4, DSM_WIRE_OUT_READY = 5 };
+typedef struct dsm_wire_out {
+  int32_t kind;
+  const char* text;     /* Word: text, Error: message (UTF-8, not NUL-terminated when decoded) */
+  int32_t text_len;
+  double time;          /* Word: start_time, EndWord: stop_time */
+  int64_t id;           /* Marker */
+  int64_t step_idx;     /* Step */
+  const float* prs;     /* Step */
+  int32_t n_prs;
+  int64_t buffered_pcm; /* Step */
+} dsm_wire_out;
+/* *len receives the encoded size; DSM_ERR_CAPACITY when it exceeds cap. */
+dsm_status dsm_wire_encode_out(const dsm_wire_out* msg, uint8_t* buf, size_t cap, size_t* len);
+dsm_status dsm_wire_decode_out(const uint8_t* bytes, size_t len, dsm_wire_out* msg, float* prs_buf, int32_t prs_cap);
+dsm_status dsm_wire_encode_in(const dsm_wire_in* msg, uint8_t* buf, size_t cap, size_t* len);
+/* Audio samples are written to pcm_buf, OggOpus bytes to data_buf; msg->pcm / msg->data point at them. */
+dsm_status dsm_wire_decode_in(const uint8_t* bytes, size_t len, dsm_wire_in* msg, float* pcm_buf, int64_t pcm_cap,
+                              uint8_t* data_buf, int64_t data_cap);
+
+/* ---- SentencePiece detokenisation (moshi-server/src/batched_asr.rs:667 decode_piece_ids) ---------------------- */
+typedef struct dsm_spm dsm_spm;
+dsm_status dsm_spm_open(const char* model_path, dsm_spm** out);
+void dsm_spm_close(dsm_spm* h);
+int32_t dsm_spm_vocab_size(const dsm_spm* h);
+const char* dsm_spm_piece(const dsm_spm* h, int32_t id);
+/* Token ids of one word -> UTF-8 text (NUL-terminated in buf); *len = length in bytes. */
+dsm_status dsm_spm_decode(dsm_spm* h, const uint32_t* ids, int32_t n, char* buf, size_t cap, size_t* len);
+
 #ifdef __cplusplus
 }
 #endif
