@@ -121,7 +121,9 @@ dsm_status dsm_debug_gemm_bf16(int32_t impl, int32_t mode, int32_t M, int32_t N,
     if (impl == 1) {
       TcGemm g;
       tc_gemm_prepare(g, dW, dX, M, N, K, mode, dO, dG);
+      if (g.partial_bytes) g.partials = a.alloc<float>(g.partial_bytes / sizeof(float), false);
       tc_gemm_launch(g, 0);
+      tc_reduce_partials(g, 0);
     } else {
       GemmParams g;
       g.A = dX, g.a_map = dense_rows(1, K), g.W = dW, g.M = M, g.N = N, g.K = K;

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 #include "../../include/dsm_b200.h"
 
@@ -53,6 +54,34 @@ inline void check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) fail(DSM_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
   DSM_LAUNCHED();
+}
+
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// Every step kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization and begins with
+//     pdl_launch_dependents();   // the next kernel of the stream / graph branch may be scheduled once all of this
+//                                // grid's CTAs have started
+//     pdl_wait();                // ... but nothing of THIS grid touches global memory before its predecessors have
+//                                // completed and flushed
+// so a kernel's launch latency, CTA rasterisation and (for the tensor-core GEMMs) barrier / TMEM / descriptor setup
+// overlap the tail of the kernel before it, inside the captured frame graph too.  A kernel launched through
+// launch_k() MUST call pdl_wait() before its first global access.  DSM_PDL=0 launches plainly (A/B).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+  }
+  DSM_CUDA(cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...));
 }
 
 // Row addressing shared by every row-wise kernel: logical row m = b * T + t lives at

@@ -5,7 +5,7 @@ namespace dsm {
 template <typename TA, typename TW, int BM, int BN, int TM, int TN>
 static void launch_cfg(const GemmParams& p, cudaStream_t st) {
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM));
-  gemm_simt_kernel<TA, TW, BM, BN, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p);
+  launch_k(gemm_simt_kernel<TA, TW, BM, BN, TM, TN>, grid, (BM / TM) * (BN / TN), 0, st, p);
   check_launch("gemm_simt");
 }
 

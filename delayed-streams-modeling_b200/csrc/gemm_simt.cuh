@@ -56,6 +56,8 @@ __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
 
 template <typename TA, typename TW, int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_simt_kernel(const GemmParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int BK = 16;
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int RM = TM / 4, RN = TN / 4;

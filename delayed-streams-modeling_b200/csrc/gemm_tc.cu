@@ -43,23 +43,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-// thread-block cluster helpers (split-K partials meet through distributed shared memory)
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_rank(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -143,7 +126,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 constexpr int TC_BN = 128;      // weight rows per CTA (UMMA M)
 constexpr int TC_BK = 64;       // bf16 per k-block = one 128-byte swizzle row
 constexpr int TC_UK = 16;       // UMMA K for 16-bit inputs
-constexpr int TC_MAX_SPLIT = 8; // split-K = cluster size (portable maximum)
+constexpr int TC_MAX_SPLIT = 16;
 
 struct TcParams {
   int M, N, K;
@@ -152,6 +135,7 @@ struct TcParams {
   int hidden;
   float* out_f32;
   __nv_bfloat16* out_bf16;
+  float* partials;   // split-K: [gridDim.z][M][N]
 };
 
 // NACC weight sub-tiles (accumulators) per CTA: the gate/value pair, or two consecutive 128-row tiles
@@ -184,6 +168,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   const int num_kb = min(p.kb_per_split, p.kb_total - kb_begin);
   const int k0 = kb_begin * TC_BK;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w);
     tma_prefetch_desc(&map_x);
@@ -201,6 +186,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above is on-chip setup; the operands and the output belong to the kernels before this one
+  pdl_wait();
 
   if (warp == 0 && elect_one()) {
     // ---------------- TMA producer ----------------
@@ -285,42 +272,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       }
     }
   } else {
-    // Split-K (NACC == 1): the gridDim.z CTAs of a tile form a thread-block cluster.  Each keeps its partial tile
-    // in TMEM, and once every CTA of the cluster is through its K loop (the pipeline stages are then free) pushes
-    // it -- st.shared::cluster, fire and forget -- into the shared memory of the CTA that owns the stream slice:
-    // rank r reduces streams [r*BMX/S, (r+1)*BMX/S) of the tile, adding the S partials IN RANK ORDER (the same sum
-    // in every run, unlike f32 atomics on the output), and applies the epilogue.  No global workspace, no spinning.
-    const uint32_t S = gridDim.z, rank = cluster_ctarank();
-    const uint32_t slice_max = (BMX + S - 1) / S;
-    const int row = warp * 32 + lane;
-    float* buf = reinterpret_cast<float*>(smem);            // [S][slice_max][128] partials of MY slice
-    cluster_sync();                                         // every CTA is done with its stages
+    // Split-K: this CTA's partial sums go to plane blockIdx.z of `partials` [S][M][N] with plain coalesced stores.
+    // They are added IN SPLIT ORDER by the kernel that consumes the result anyway (RMSNorm for the residual
+    // projections, RoPE + ring scatter for QKV, the greedy argmax for the text head; tc_reduce_partials for a
+    // stand-alone GEMM), so the sum is the same in every run -- no atomics -- and costs no extra launch.
+    const int n = n0 + warp * 32 + lane;
+    float* plane = p.partials + (size_t)blockIdx.z * p.M * p.N;
 #pragma unroll 1
     for (int c = 0; c < BMX; c += 32) {
       if (m0 + c >= p.M) break;
       float v[32];
       tmem_ld32(lane_addr + c, v);
+      if (n < p.N) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const uint32_t mm = c + i;
-        uint32_t owner = mm * S / BMX;                      // slice r = streams [ceil(r*BMX/S), ceil((r+1)*BMX/S))
-        if (((owner + 1) * BMX + S - 1) / S <= mm) ++owner;
-        const uint32_t local = mm - (owner * BMX + S - 1) / S;
-        st_cluster_f32(map_to_rank(smem_u32(buf + ((size_t)rank * slice_max + local) * TC_BN + row), owner), v[i]);
-      }
-    }
-    cluster_sync();                                         // all partials have landed
-    const int n = n0 + row;
-    const uint32_t mm0 = (rank * BMX + S - 1) / S, mm1 = ((rank + 1) * BMX + S - 1) / S;
-    if (n < p.N) {
-#pragma unroll 4
-      for (uint32_t mm = mm0; mm < mm1; ++mm) {
-        if (m0 + (int)mm >= p.M) break;
-        float acc = 0.f;
-        for (uint32_t sp = 0; sp < S; ++sp) acc += buf[((size_t)sp * slice_max + (mm - mm0)) * TC_BN + row];
-        float* dst = p.out_f32 + (long long)(m0 + mm) * p.N + n;
-        if (MODE == TC_STORE_F32) *dst = acc;
-        else *dst += acc;
+        for (int i = 0; i < 32; ++i) {
+          const int m = m0 + c + i;
+          if (m < p.M) plane[(long long)m * p.N + n] = v[i];
+        }
       }
     }
   }
@@ -388,49 +356,12 @@ static void launch_tc(const TcGemm& g, cudaStream_t st) {
   p.kb_total = g.K / TC_BK;
   p.kb_per_split = ceil_div(p.kb_total, g.split_k);
   DSM_CHECK(ceil_div(p.kb_total, p.kb_per_split) == g.split_k, DSM_ERR_INVALID_ARG, "tc_gemm: split_k %d leaves an empty split", g.split_k);
-  p.out_f32 = g.out_f32, p.out_bf16 = g.out_bf16;
+  p.out_f32 = g.out_f32, p.out_bf16 = g.out_bf16, p.partials = g.partials;
   const int n_rows = MODE == TC_GATE_BF16 ? g.hidden : g.N;
   dim3 grid(ceil_div(n_rows, TC_BN * (MODE == TC_GATE_BF16 ? 1 : NACC)), ceil_div(g.M, BMX), g.split_k);
-  DSM_CHECK(g.split_k == 1 || (NACC == 1 && g.split_k <= TC_MAX_SPLIT), DSM_ERR_INVALID_ARG, "tc_gemm: split_k %d", g.split_k);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid, cfg.blockDim = dim3(128), cfg.dynamicSmemBytes = C::SMEM, cfg.stream = st;
-  cudaLaunchAttribute attrs[1];
-  if (g.split_k > 1) {
-    attrs[0].id = cudaLaunchAttributeClusterDimension;     // the splits of a tile are one cluster
-    attrs[0].val.clusterDim.x = 1, attrs[0].val.clusterDim.y = 1, attrs[0].val.clusterDim.z = (unsigned)g.split_k;
-    cfg.attrs = attrs, cfg.numAttrs = 1;
-  }
-  DSM_CUDA(cudaLaunchKernelEx(&cfg, kern, g.map_w, g.map_x, p));
+  DSM_CHECK(g.split_k == 1 || (NACC == 1 && g.partials), DSM_ERR_INVALID_ARG, "tc_gemm: split_k %d without a partials buffer", g.split_k);
+  launch_k(kern, grid, 128, C::SMEM, st, g.map_w, g.map_x, p);
   check_launch("tc_gemm");
-}
-
-// Clusters of `split` CTAs of this configuration the device can hold at once.
-template <int BMX, int MODE>
-static int cluster_capacity(int split) {
-  using C = TcCfg<BMX, MODE, 1>;
-  auto kern = tc_gemm_kernel<BMX, MODE, 1, C::STAGES>;
-  static PerDeviceOnce attr;
-  attr.run([&] { DSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); });
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(1, 1, split), cfg.blockDim = dim3(128), cfg.dynamicSmemBytes = C::SMEM;
-  cudaLaunchAttribute a[1];
-  a[0].id = cudaLaunchAttributeClusterDimension;
-  a[0].val.clusterDim.x = 1, a[0].val.clusterDim.y = 1, a[0].val.clusterDim.z = (unsigned)split;
-  cfg.attrs = a, cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
-  }
-  return n;
-}
-static int tc_cluster_capacity(int bmx, int mode, int split) {
-#define CAP_CASE(BMX, MODE) \
-  if (bmx == BMX && mode == MODE) return cluster_capacity<BMX, MODE>(split);
-  CAP_CASE(64, TC_STORE_F32) CAP_CASE(128, TC_STORE_F32) CAP_CASE(256, TC_STORE_F32)
-  CAP_CASE(64, TC_ACCUM_F32) CAP_CASE(128, TC_ACCUM_F32) CAP_CASE(256, TC_ACCUM_F32)
-#undef CAP_CASE
-  return 0;
 }
 
 void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, int M, int N, int K, int mode,
@@ -440,52 +371,60 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
   g.M = M, g.N = N, g.K = K, g.mode = mode, g.out_f32 = out_f32, g.out_bf16 = out_bf16;
   g.hidden = mode == TC_GATE_BF16 ? N / 2 : 0;
   const int n_rows = mode == TC_GATE_BF16 ? g.hidden : N;
-  // Wide CTAs (two weight sub-tiles per CTA) halve the activation re-reads but also halve the CTA count
-  // and double the epilogue; measured slower at 256 streams (LM step 5.85 ms vs 5.15 ms), so they are
-  // opt-in (DSM_TC_WIDE=1) for experiments with larger batches.
-  static const bool wide = [] { const char* e = getenv("DSM_TC_WIDE"); return e && e[0] == '1'; }();
-  g.nacc = mode == TC_GATE_BF16 ? 2 : ((wide && n_rows >= 2 * TC_BN) ? 2 : 1);
+  g.nacc = mode == TC_GATE_BF16 ? 2 : 1;
   const int n_tiles = ceil_div(n_rows, TC_BN * (mode == TC_GATE_BF16 ? 1 : g.nacc));
   // Stream tile: as wide as the batch allows.  Every CTA must pull its W slab AND its X slab through
   // the SM's L2 port, so narrower stream tiles multiply the X traffic; to cover the 148 SMs we split K
-  // instead (same total bytes, more CTAs): the splits of a tile form a cluster and add their partial tiles
-  // through distributed shared memory in rank order (deterministic).  The gate pair has a non-linear epilogue, so it does not split.
-  g.bmx = M <= 64 ? 64 : (M <= 128 ? 128 : ((mode == TC_GATE_BF16 && !wide) ? 128 : 256));
-  // experiment knobs: DSM_TC_BMX forces the stream tile, DSM_TC_MAXSPLIT caps split-K
-  static const int env_bmx = [] { const char* e = getenv("DSM_TC_BMX"); return e ? atoi(e) : 0; }();
+  // instead (same total bytes, more CTAs); the partial sums are added in split order by the consuming kernel
+  // (deterministic).  The gate pair has a non-linear epilogue, so it does not split.
+  g.bmx = M <= 64 ? 64 : (M <= 128 ? 128 : (mode == TC_GATE_BF16 ? 128 : 256));
+  // DSM_TC_MAXSPLIT caps split-K (1 = no split: A/B of the partial-sum path)
   static const int env_split = [] { const char* e = getenv("DSM_TC_MAXSPLIT"); return e ? std::min(atoi(e), TC_MAX_SPLIT) : TC_MAX_SPLIT; }();
-  if (env_bmx && mode != TC_GATE_BF16 && M > env_bmx / 2) g.bmx = env_bmx;
   g.split_k = 1;
-  if (mode != TC_GATE_BF16 && g.nacc == 1) {
-    // Pick the split by a cost model in k-block units: a CTA costs a fixed prologue + pipeline fill + epilogue
-    // (~10 k-blocks' worth at 256 streams) plus its K slice, and the grid runs in as many waves as the SMs -- or, for
-    // clusters, the GPCs (16-20 SMs each: cudaOccupancyMaxActiveClusters) -- can hold at once.
+  if (mode != TC_GATE_BF16) {
+    // fill the 148 SMs by splitting K (at least 4 k-blocks per split)
     const int kb = K / TC_BK;
-    const long long tiles = (long long)n_tiles * ceil_div(M, g.bmx);
-    double best = 1e30;
+    const long long base = (long long)n_tiles * ceil_div(M, g.bmx);
+    double best = 0.0;
     for (int s = 1; s <= env_split; ++s) {
       const int per = ceil_div(kb, s);
       if (per < 4 && s > 1) break;
       const int s_eff = ceil_div(kb, per);
-      if (s_eff != s) continue;
-      const long long per_wave = s == 1 ? 148 : tc_cluster_capacity(g.bmx, mode, s);
-      if (per_wave <= 0) continue;
-      const double cost = (double)ceil_div(tiles, per_wave) * (10.0 + per);
-      if (cost < best * 0.98) best = cost, g.split_k = s;
+      const long long ctas = base * s_eff;
+      const double eff = (double)ctas / (double)(ceil_div(ctas, 148LL) * 148);
+      if (eff > best + 0.02) best = eff, g.split_k = s_eff;
     }
   }
+  g.partial_bytes = g.split_k > 1 ? (size_t)g.split_k * M * N * sizeof(float) : 0;
   make_map(&g.map_w, W, (uint64_t)N, (uint64_t)K, TC_BN);
   make_map(&g.map_x, X, (uint64_t)M, (uint64_t)K, (uint32_t)g.bmx);
+}
+
+// out[m, n] (+)= sum_s partials[s][m][n], in split order: for GEMMs whose consumer does not do it (debug entry).
+__global__ void tc_reduce_partials_kernel(const float* __restrict__ partials, int S, long long MN, int accumulate,
+                                          float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < MN; i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += partials[(long long)s * MN + i];
+    out[i] = accumulate ? out[i] + acc : acc;
+  }
+}
+void tc_reduce_partials(const TcGemm& g, cudaStream_t st) {
+  if (g.split_k <= 1) return;
+  const long long MN = (long long)g.M * g.N;
+  launch_k(tc_reduce_partials_kernel, (unsigned)std::min<long long>(ceil_div(MN, 256LL), 148 * 8), 256, 0, st, g.partials, g.split_k, MN,
+           g.mode == TC_ACCUM_F32 ? 1 : 0, g.out_f32);
+  check_launch("tc_reduce_partials");
 }
 
 void tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
 #define TC_CASE(BMX, MODE, NACC) \
   if (g.bmx == BMX && g.mode == MODE && g.nacc == NACC) return launch_tc<BMX, MODE, NACC>(g, st);
   TC_CASE(64, TC_STORE_F32, 1) TC_CASE(128, TC_STORE_F32, 1) TC_CASE(256, TC_STORE_F32, 1)
-  TC_CASE(64, TC_STORE_F32, 2) TC_CASE(128, TC_STORE_F32, 2) TC_CASE(256, TC_STORE_F32, 2)
   TC_CASE(64, TC_ACCUM_F32, 1) TC_CASE(128, TC_ACCUM_F32, 1) TC_CASE(256, TC_ACCUM_F32, 1)
-  TC_CASE(64, TC_ACCUM_F32, 2) TC_CASE(128, TC_ACCUM_F32, 2) TC_CASE(256, TC_ACCUM_F32, 2)
-  TC_CASE(64, TC_GATE_BF16, 2) TC_CASE(128, TC_GATE_BF16, 2) TC_CASE(256, TC_GATE_BF16, 2)
+  TC_CASE(64, TC_GATE_BF16, 2) TC_CASE(128, TC_GATE_BF16, 2)
 #undef TC_CASE
   fail(DSM_ERR_UNSUPPORTED, "tc_gemm: no kernel for bmx=%d mode=%d nacc=%d", g.bmx, g.mode, g.nacc);
 }

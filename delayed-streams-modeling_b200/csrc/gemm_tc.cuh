@@ -9,8 +9,8 @@
 //   warp 2            : TMEM alloc / dealloc
 //   warps 0-3         : epilogue -- tcgen05.ld of the warp's 32 TMEM lanes, fused op, coalesced stores
 // Epilogues: plain f32 store (QKV, text head), residual accumulate x += acc (out-proj, MLP-out; with
-// split-K the CTAs of a tile form a thread-block cluster and add their partial tiles through distributed shared
-// memory in rank order, so results are bit-reproducible from run to run), and the gated-MLP pair
+// split-K every split stores its partial tile and the kernel that consumes the result adds the partials in split
+// order, so results are bit-reproducible from run to run), and the gated-MLP pair
 // silu(gate) * value -> bf16, where the CTA accumulates gate rows [j0, j0+128) and value rows
 // [hidden + j0, ...) side by side in TMEM (batched_transformer.rs:170-176).
 #pragma once
@@ -32,14 +32,19 @@ struct TcGemm {
   int split_k = 1;
   int mode = TC_STORE_F32;
   int hidden = 0;      // TC_GATE_BF16: N = 2 * hidden
-  float* out_f32 = nullptr;            // STORE: [M, N];  ACCUM: x [M, N] (+=)
+  float* out_f32 = nullptr;            // STORE: [M, N];  ACCUM: x [M, N] (+=)   (split_k == 1, or after tc_reduce_partials)
   __nv_bfloat16* out_bf16 = nullptr;   // GATE: [M, hidden]
+  // split_k > 1: the kernel writes partial sums to partials [split_k][M][N] (partial_bytes, set by prepare; the
+  // caller binds the memory) and the CONSUMER of the result adds them in split order -- see lm.cu
+  size_t partial_bytes = 0;
+  float* partials = nullptr;
 };
 
 // Builds the tensor maps and picks the tile / split-K so the grid covers the 148 SMs.
 void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, int M, int N, int K, int mode,
                      float* out_f32, __nv_bfloat16* out_bf16);
 void tc_gemm_launch(const TcGemm& g, cudaStream_t st);
+void tc_reduce_partials(const TcGemm& g, cudaStream_t st);   // out (+)= sum of the partial planes, in split order
 bool tc_gemm_supported(int M, int N, int K, int mode);
 
 }  // namespace dsm

@@ -193,9 +193,6 @@ constexpr int T6_PLANE = T6_BM * T6_BK * 2;      // 16 KB per bf16 plane tile
 constexpr int T6_EPI_WARPS = 8;      // two per TMEM lane quadrant
 constexpr int T6_CVT_WARPS = 4;      // one converter thread per tile row
 constexpr int T6_THREADS = (4 + T6_CVT_WARPS + T6_EPI_WARPS) * 32;
-// Optional minimum spacing of the 4-MMA issue groups in cycles (DSM_TC6_PACE64/32; 0 = off, the default).  It was
-// the first, wrong, explanation of the corrupted tiles that the proxy fence in the converter warps cured; kept as
-// an A/B switch.
 #ifndef T6_TS
 #define T6_TS 1
 #endif
@@ -224,7 +221,6 @@ struct Tc6Params {
   int nj;              // column sub-tiles per tile
   int pm;              // main-term accumulators the k-blocks rotate over (see the MMA issuer)
   int split_k;         // K splits per tile (work item = (tile, split)); partials meet in `ws`
-  int pace;            // minimum cycles between 4-MMA issue groups
   int acc_bufs;        // accumulator tile buffers in TMEM (1 or 2)
   float* ws;           // [tiles * split_k][128][nj * BN] partial sums (split_k > 1)
   int* counters;       // [tiles] arrivals; the last split to arrive reduces in split order and stores
@@ -288,6 +284,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int kb_per = (num_kb + S - 1) / S;       // the host picks S so that no split is empty
   const int total_items = total_tiles * S;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_w);
@@ -316,6 +313,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // on-chip setup above; operands, residual and outputs belong to the kernels before this one
 
   if (warp == 0 && elect_one()) {
     // ---------------- A producer: f32 conv-window tile -> staging ----------------
@@ -370,7 +368,6 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int pa[6] = {0, 1, 2, 0, 1, 0};
     const int pw[6] = {2, 1, 0, 1, 0, 0};
     int kit = 0, wit = 0, li = 0;
-    long long t_grp = clock64() - p.pace;   // issue time of the last MMA group
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
       const int tile = item / S, kbn = min(kb_per, num_kb - (item % S) * kb_per);
       const int pm = min(p.pm, kbn);                       // main accumulators actually written
@@ -397,12 +394,6 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint64_t dw = make_smem_desc(w_base + pw[t] * (BN * T6_BK * 2));
             const int set = t < 5 ? 0 : 1 + kb % pm;
             const bool first = t < 5 ? (kb == 0 && t == 0) : (kb < pm);
-            // optional issue pacing (off by default, see T6 pacing note above)
-            if (p.pace > 0) {
-              while (clock64() - t_grp < p.pace) {
-              }
-              t_grp = clock64();
-            }
 #pragma unroll
             for (int k = 0; k < T6_BK / 16; ++k) {
               if (TS)
@@ -739,9 +730,6 @@ static void launch6(const Tc6Gemm& g, cudaStream_t st) {
   p.m_tiles = p.t_tiles * ceil_div(g.B, g.b_sub);
   p.n_groups = ceil_div(g.N, g.nj * BN);
   p.split_k = g.split_k, p.ws = g.ws, p.counters = g.counters;
-  static const int pace64 = [] { const char* e = getenv("DSM_TC6_PACE64"); return e ? atoi(e) : 0; }();
-  static const int pace32 = [] { const char* e = getenv("DSM_TC6_PACE32"); return e ? atoi(e) : 0; }();
-  p.pace = BN == 64 ? pace64 : pace32;
   p.acc_bufs = g.acc_bufs;
   p.bias = g.ep.bias, p.neg = g.ep.neg, p.scale = g.ep.scale, p.res = g.ep.res, p.r_map = g.ep.r_map, p.act = g.ep.act;
   p.out_raw = g.ep.out_raw, p.o_map = g.ep.o_map, p.out_act = g.ep.out_act, p.e_map = g.ep.e_map;
@@ -749,7 +737,7 @@ static void launch6(const Tc6Gemm& g, cudaStream_t st) {
   const long long tiles = (long long)p.m_tiles * p.n_groups * g.split_k;
   static const int max_ctas = [] { const char* e = getenv("DSM_TC6_MAXCTAS"); int v = e ? atoi(e) : 0; return v > 0 ? v : 148; }();
   const int grid = (int)std::min<long long>(tiles, max_ctas);
-  kern<<<grid, T6_THREADS, C::SMEM, st>>>(g.map_a, g.map_w, p);
+  launch_k(kern, grid, T6_THREADS, C::SMEM, st, g.map_a, g.map_w, p);
   check_launch("tc6_gemm");
 }
 

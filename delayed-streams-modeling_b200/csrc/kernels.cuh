@@ -99,10 +99,19 @@ void launch_upsample_dw(const float* x, const float* state, const float* w /*[C,
 void launch_embed_sum(const uint32_t* text_ids, const uint32_t* audio_ids, int n_cb, const __nv_bfloat16* text_emb,
                       int text_vocab, const __nv_bfloat16* audio_emb /*[n_cb][audio_vocab][D]*/, int audio_vocab,
                       const float* cond, int B, int D, float* x, cudaStream_t st);
-void launch_rmsnorm(const float* x, const float* alpha, float eps, int B, int D, __nv_bfloat16* out_bf16,
+// Split-K partial sums of a projection ([count][rows][cols] f32 planes `stride` elements apart, gemm_tc.cuh) that the
+// consuming kernel adds in split order; count == 0: the projection wrote its result directly.
+struct PartialSums {
+  const float* planes = nullptr;
+  int count = 0;
+  long long stride = 0;
+};
+// x <- x + sum of the partial planes (if any), then RMSNorm of x -> out_bf16 / out_f32
+void launch_rmsnorm(float* x, const PartialSums& ps, const float* alpha, float eps, int B, int D, __nv_bfloat16* out_bf16,
                     float* out_f32, cudaStream_t st);
-// qkv f32 [B, 3*H*D] -> q bf16 [B, H*D] (rotated); rotated k, v -> bf16 rings [B,H,ctx,D] at cur_index[b].
-void launch_rope_scatter_bf16(const float* qkv, const RingState& rs, int B, int H, int D, int context,
+// qkv f32 [B, 3*H*D] (or its partial planes) -> q bf16 [B, H*D] (rotated); rotated k, v -> bf16 rings [B,H,ctx,D] at
+// cur_index[b].
+void launch_rope_scatter_bf16(const float* qkv, const PartialSums& ps, const RingState& rs, int B, int H, int D, int context,
                               const float* inv_freq /*[D/2]*/,
                               __nv_bfloat16* q_out, __nv_bfloat16* k_ring, __nv_bfloat16* v_ring, cudaStream_t st);
 void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint8_t* mask, int B, int H, int D,
@@ -118,14 +127,15 @@ struct KvRingQ8 {
   __nv_bfloat16* v_bf16;
   int ctxp;   // context rounded up to a multiple of 4
 };
-void launch_rope_scatter_q8(const float* qkv, const RingState& rs, int B, int H, int D, int context, const float* inv_freq,
-                            __nv_bfloat16* q_out, const KvRingQ8& ring, cudaStream_t st);
+void launch_rope_scatter_q8(const float* qkv, const PartialSums& ps, const RingState& rs, int B, int H, int D, int context,
+                            const float* inv_freq, __nv_bfloat16* q_out, const KvRingQ8& ring, cudaStream_t st);
 void launch_lm_attention_q8(const __nv_bfloat16* q, const RingState& rs, const uint8_t* mask, int B, int H, int D, int context,
                             const KvRingQ8& ring, __nv_bfloat16* out, cudaStream_t st);
 // h f32 [B, 2*Hd] -> g bf16 [B, Hd] = silu(h[:, :Hd]) * h[:, Hd:]   (batched_transformer.rs:170-176)
 void launch_silu_gate(const float* h, int B, int Hd, __nv_bfloat16* g, cudaStream_t st);
-// greedy sampling (asr.rs:208-210): first argmax over logits [B, V]
-void launch_argmax(const float* logits, int B, int V, uint32_t* tokens, cudaStream_t st);
+// greedy sampling (asr.rs:208-210): first argmax over logits [B, V]; partial planes of the text head are summed into
+// `logits` on the way
+void launch_argmax(float* logits, const PartialSums& ps, int B, int V, uint32_t* tokens, cudaStream_t st);
 // extra heads (lm.rs:948-955 + asr.rs:195-206): prs[h*B + b] = softmax(W_h . ys[b])[0]
 void launch_extra_heads(const __nv_bfloat16* ys, const __nv_bfloat16* w /*[nh][dim][D]*/, int nh, int dim, int B, int D,
                         float* prs, cudaStream_t st);

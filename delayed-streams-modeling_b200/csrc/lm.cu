@@ -42,13 +42,7 @@ LmImpl::LmImpl(const dsm_lm_spec& sp, const dsm_weights* w, int dev, int batch, 
   hidden = sp.dim_feedforward == 4 * D ? 11 * D / 4 : 2 * sp.dim_feedforward / 3;   // batched_transformer.rs:153-157
   DSM_CHECK(hidden % 16 == 0, DSM_ERR_UNSUPPORTED, "gated hidden size %d must be a multiple of 16", hidden);
   DSM_CUDA(cudaSetDevice(device));
-  {
-    // DSM_LM_PRIORITY=1: the LM branch is the longer one of the frame graph; let its CTAs win the SMs.
-    const char* e = getenv("DSM_LM_PRIORITY");
-    int lo = 0, hi = 0;
-    DSM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    DSM_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, (e && e[0] == '1') ? hi : (e && e[0] == '2') ? lo : 0));
-  }
+  DSM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   WeightTable wt(w);
   const bool random = (w == nullptr);
 
@@ -162,6 +156,7 @@ LmImpl::LmImpl(const dsm_lm_spec& sp, const dsm_weights* w, int dev, int batch, 
   ys_bf16 = arena.alloc<__nv_bfloat16>((size_t)B * D);
   ys_f32 = arena.alloc<float>((size_t)B * D);
   logits = arena.alloc<float>((size_t)B * sp.text_out_vocab_size);
+  d_sampled = arena.alloc<uint32_t>(B);
 
   {
     const char* e = getenv("DSM_LM_GEMM");
@@ -176,6 +171,17 @@ LmImpl::LmImpl(const dsm_lm_spec& sp, const dsm_weights* w, int dev, int batch, 
       tc_gemm_prepare(y.g_down, y.lin_out, gbuf, B, D, hidden, TC_ACCUM_F32, x, nullptr);
     }
     tc_gemm_prepare(g_text, text_linear, ys_bf16, B, sp.text_out_vocab_size, D, TC_STORE_F32, logits, nullptr);
+    // one buffer for the split-K partial planes of all of them: each GEMM's partials are consumed by the very next
+    // kernel of the stream (RMSNorm / RoPE-scatter / argmax) before the following GEMM writes its own
+    std::vector<TcGemm*> all{&g_text};
+    for (Layer& y : layers)
+      for (TcGemm* g : {&y.g_qkv, &y.g_out, &y.g_in, &y.g_down}) all.push_back(g);
+    size_t bytes = 0;
+    for (TcGemm* g : all) bytes = std::max(bytes, g->partial_bytes);
+    if (bytes) {
+      float* buf = arena.alloc<float>(bytes / sizeof(float), false);
+      for (TcGemm* g : all) g->partials = buf;
+    }
   }
   build_plan(plan, false);
   build_plan(plan_cond, true);
@@ -194,6 +200,12 @@ LmImpl::~LmImpl() {
   if (stream) cudaStreamDestroy(stream);
 }
 
+static PartialSums partial_sums(const TcGemm& g, bool use_tc) {
+  PartialSums ps;
+  if (use_tc && g.split_k > 1) ps.planes = g.partials, ps.count = g.split_k, ps.stride = (long long)g.M * g.N;
+  return ps;
+}
+
 void LmImpl::build_plan(Plan& p, bool with_cond) {
   LmImpl* s = this;
   const float* cond = with_cond ? d_cond : nullptr;
@@ -202,11 +214,15 @@ void LmImpl::build_plan(Plan& p, bool with_cond) {
     launch_embed_sum(s->d_text_ids, s->d_audio_ids, s->spec.audio_codebooks, s->text_emb, s->spec.text_in_vocab_size,
                      s->audio_emb, s->spec.audio_vocab_size, cond, s->B, s->D, s->x, st);
   });
+  // Split-K partial planes a residual projection left behind: the next RMSNorm folds them into x (gemm_tc.cuh).
+  PartialSums pending;
   for (int l = 0; l < L; ++l) {
     const Layer y = layers[l];
+    const PartialSums ps_in = pending, ps_qkv = partial_sums(y.g_qkv, use_tc), ps_out = partial_sums(y.g_out, use_tc);
+    pending = partial_sums(y.g_down, use_tc);
     p.push_back([=](cudaStream_t st) {
       const int B = s->B, D = s->D, Hd = s->hidden;
-      launch_rmsnorm(s->x, y.norm1, s->spec.rms_eps, B, D, s->xn, nullptr, st);
+      launch_rmsnorm(s->x, ps_in, y.norm1, s->spec.rms_eps, B, D, s->xn, nullptr, st);
       if (s->use_tc) {
         tc_gemm_launch(y.g_qkv, st);
       } else {
@@ -216,28 +232,28 @@ void LmImpl::build_plan(Plan& p, bool with_cond) {
         launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(g, st);
       }
       if (s->kv_dtype != DSM_KV_BF16) {
-        launch_rope_scatter_q8(s->qkv, s->ring, B, s->H, s->hd, s->ctx, s->inv_freq, s->q, y.q8, st);
+        launch_rope_scatter_q8(s->qkv, ps_qkv, s->ring, B, s->H, s->hd, s->ctx, s->inv_freq, s->q, y.q8, st);
         s->profile_begin(st);
         launch_lm_attention_q8(s->q, s->ring, s->d_mask, B, s->H, s->hd, s->ctx, y.q8, s->attn, st);
         s->profile_end(st);
       } else {
-        launch_rope_scatter_bf16(s->qkv, s->ring, B, s->H, s->hd, s->ctx, s->inv_freq, s->q, y.k_ring, y.v_ring, st);
+        launch_rope_scatter_bf16(s->qkv, ps_qkv, s->ring, B, s->H, s->hd, s->ctx, s->inv_freq, s->q, y.k_ring, y.v_ring, st);
         s->profile_begin(st);
         launch_lm_attention(s->q, s->ring, s->d_mask, B, s->H, s->hd, s->ctx, y.k_ring, y.v_ring, s->attn, st);
         s->profile_end(st);
       }
       if (s->use_tc) {
-        tc_gemm_launch(y.g_out, st);       // x += out_proj(attn)
+        tc_gemm_launch(y.g_out, st);       // x += out_proj(attn)   (or its partial planes)
       } else {
         GemmParams o;
         o.A = s->attn, o.a_map = dense_rows(1, D), o.W = y.out_proj, o.M = B, o.N = D, o.K = D;
         o.res = s->x, o.r_map = dense_rows(1, D), o.out_raw = s->x, o.o_map = dense_rows(1, D);
         launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(o, st);
       }
-      launch_rmsnorm(s->x, y.norm2, s->spec.rms_eps, B, D, s->xn, nullptr, st);
+      launch_rmsnorm(s->x, ps_out, y.norm2, s->spec.rms_eps, B, D, s->xn, nullptr, st);
       if (s->use_tc) {
         tc_gemm_launch(y.g_in, st);        // gbuf = silu(gate) * value
-        tc_gemm_launch(y.g_down, st);      // x += linear_out(gbuf)
+        tc_gemm_launch(y.g_down, st);      // x += linear_out(gbuf)   (or its partial planes)
       } else {
         GemmParams f1;
         f1.A = s->xn, f1.a_map = dense_rows(1, D), f1.W = y.lin_in, f1.M = B, f1.N = 2 * Hd, f1.K = D;
@@ -251,9 +267,10 @@ void LmImpl::build_plan(Plan& p, bool with_cond) {
       }
     });
   }
+  const PartialSums ps_last = pending, ps_text = partial_sums(g_text, use_tc);
   p.push_back([=](cudaStream_t st) {
     const int B = s->B, D = s->D, V = s->spec.text_out_vocab_size;
-    launch_rmsnorm(s->x, s->out_norm, s->spec.rms_eps, B, D, s->ys_bf16, s->ys_f32, st);
+    launch_rmsnorm(s->x, ps_last, s->out_norm, s->spec.rms_eps, B, D, s->ys_bf16, s->ys_f32, st);
     if (s->use_tc) {
       tc_gemm_launch(s->g_text, st);
     } else {
@@ -262,6 +279,8 @@ void LmImpl::build_plan(Plan& p, bool with_cond) {
       g.out_raw = s->logits, g.o_map = dense_rows(1, V);
       launch_gemm_simt<__nv_bfloat16, __nv_bfloat16>(g, st);
     }
+    // greedy token (asr.rs:208-210); also where the text head's partial planes become the logits
+    launch_argmax(s->logits, ps_text, B, V, s->d_sampled, st);
   });
 }
 
@@ -363,13 +382,13 @@ AsrImpl::AsrImpl(MimiImpl* mi, LmImpl* l, int dly, float temperature) : mimi(mi)
   text_tok = arena.alloc<uint32_t>(B);
   first_step = arena.alloc<uint8_t>(B);
   codes_in = arena.alloc<uint32_t>((size_t)B * n_cb);
-  sampled = arena.alloc<uint32_t>(B);
+  sampled = lm->d_sampled;          // greedy tokens: the last kernel of the LM plan
   prs = arena.alloc<float>((size_t)std::max(nh, 1) * B);
   h_sampled = static_cast<uint32_t*>(arena.alloc_pinned((size_t)B * 4));
   h_prs = static_cast<float*>(arena.alloc_pinned((size_t)std::max(nh, 1) * B * 4));
   h_mask.assign(B, 1);
   items.resize(B);
-  for (cudaEvent_t* e : {&ev_fork, &ev_join, &ev_seanet}) DSM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  for (cudaEvent_t* e : {&ev_fork, &ev_join}) DSM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   for (cudaEvent_t* e : {&ev_t0, &ev_t1, &ev_m0, &ev_m1, &ev_l0, &ev_l1}) DSM_CUDA(cudaEventCreate(e));
   reset();
 }
@@ -380,7 +399,7 @@ AsrImpl::~AsrImpl() {
   if (mimi) cudaStreamSynchronize(mimi->stream);
   graph_pcm.reset();
   graph_tokens.reset();
-  for (cudaEvent_t e : {ev_fork, ev_join, ev_seanet, ev_t0, ev_t1, ev_m0, ev_m1, ev_l0, ev_l1})
+  for (cudaEvent_t e : {ev_fork, ev_join, ev_t0, ev_t1, ev_m0, ev_m1, ev_l0, ev_l1})
     if (e) cudaEventDestroy(e);
 }
 
@@ -426,25 +445,13 @@ void AsrImpl::enqueue(bool with_mimi, bool timing) {
     DSM_CUDA(cudaEventRecord(ev_fork, sl));
     DSM_CUDA(cudaStreamWaitEvent(sm, ev_fork, 0));
     if (timing) DSM_CUDA(cudaEventRecord(ev_m0, sm));
-    // DSM_ASR_SEANET_FIRST=1: the LM branch starts only when the SEANet encoder is through.  Its GEMMs take every
-    // SM (persistent 148-CTA grids) and the LM's attention takes every byte of HBM bandwidth; run side by side they
-    // only get in each other's way, while the codec's transformer and RVQ (few CTAs per launch) do overlap the LM.
-    static const bool seanet_first = [] { const char* e = getenv("DSM_ASR_SEANET_FIRST"); return e && e[0] == '1'; }();
-    if (seanet_first && mimi->enc_seanet_end > 0 && mimi->enc_seanet_end < mimi->enc_plan.size()) {
-      for (size_t i = 0; i < mimi->enc_seanet_end; ++i) mimi->enc_plan[i](sm);
-      DSM_CUDA(cudaEventRecord(ev_seanet, sm));
-      DSM_CUDA(cudaStreamWaitEvent(sl, ev_seanet, 0));
-      for (size_t i = mimi->enc_seanet_end; i < mimi->enc_plan.size(); ++i) mimi->enc_plan[i](sm);
-    } else {
-      run_plan(mimi->enc_plan, sm);
-    }
+    run_plan(mimi->enc_plan, sm);
     if (timing) DSM_CUDA(cudaEventRecord(ev_m1, sm));
     DSM_CUDA(cudaEventRecord(ev_join, sm));
   }
   if (timing) DSM_CUDA(cudaEventRecord(ev_l0, sl));
   launch_asr_prepare(next_cb, first_step, text_tok, pad, start, B, n_cb, lm->d_audio_ids, lm->d_text_ids, sl);
   run_plan(lm->plan, sl);
-  launch_argmax(lm->logits, B, lm->spec.text_out_vocab_size, sampled, sl);
   if (nh > 0)
     launch_extra_heads(lm->ys_bf16, lm->extra_w, nh, lm->spec.extra_heads_dim, B, lm->D, prs, sl);
   if (timing) DSM_CUDA(cudaEventRecord(ev_l1, sl));

@@ -57,6 +57,7 @@ struct LmImpl {
   __nv_bfloat16* ys_bf16 = nullptr;     // [B, D]
   float* ys_f32 = nullptr;              // [B, D]
   float* logits = nullptr;              // [B, V]
+  uint32_t* d_sampled = nullptr;        // [B] greedy argmax of the logits (last kernel of the plan)
 
   // optional per-launch timing of the attention kernel (bench.py's roofline leg; eager mode only)
   bool profile_attn = false;
@@ -114,7 +115,7 @@ struct AsrImpl {
   std::vector<ItemState> items;
   std::vector<AsrMsgStore> msgs;
   std::vector<float> prs_copy;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_seanet = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_m0 = nullptr, ev_m1 = nullptr,
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_m0 = nullptr, ev_m1 = nullptr,
               ev_l0 = nullptr, ev_l1 = nullptr;
   GraphExec graph_pcm, graph_tokens;
   float last_ms[3] = {-1.f, -1.f, -1.f};

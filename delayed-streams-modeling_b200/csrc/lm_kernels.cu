@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(256) embed_sum_kernel(const uint32_t* __restri
                                                          const __nv_bfloat16* __restrict__ text_emb, int text_vocab,
                                                          const __nv_bfloat16* __restrict__ audio_emb, int audio_vocab,
                                                          const float* __restrict__ cond, int D, float* __restrict__ x) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   uint32_t tid_text = text_ids[b];
   if (tid_text >= (uint32_t)text_vocab) tid_text = text_vocab - 1;
@@ -47,7 +49,7 @@ void launch_embed_sum(const uint32_t* text_ids, const uint32_t* audio_ids, int n
                       int text_vocab, const __nv_bfloat16* audio_emb, int audio_vocab, const float* cond, int B, int D,
                       float* x, cudaStream_t st) {
   DSM_CHECK(D % 8 == 0, DSM_ERR_UNSUPPORTED, "embed_sum: D=%d", D);
-  embed_sum_kernel<<<B, 256, 0, st>>>(text_ids, audio_ids, n_cb, text_emb, text_vocab, audio_emb, audio_vocab, cond, D, x);
+  launch_k(embed_sum_kernel, B, 256, 0, st, text_ids, audio_ids, n_cb, text_emb, text_vocab, audio_emb, audio_vocab, cond, D, x);
   check_launch("embed_sum");
 }
 
@@ -55,15 +57,29 @@ void launch_embed_sum(const uint32_t* text_ids, const uint32_t* audio_ids, int n
 // RMSNorm (batched_transformer.rs:181-198, eps 1e-8): x * rsqrt(mean(x^2) + eps) * alpha, f32 math,
 // bf16 (GEMM operand) and optional f32 outputs.  One CTA per stream.
 // ================================================================================================
-__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
-                                                       float eps, int D, __nv_bfloat16* __restrict__ out_bf16,
+// Split-K partial sums of the projection that precedes the norm ([S][B][D] planes, see gemm_tc.cuh) are folded into
+// the residual stream here, in split order: x <- x + (P_0 + P_1 + ... + P_{S-1}).
+__global__ void __launch_bounds__(256) rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ partials, int S,
+                                                       long long part_stride, const float* __restrict__ alpha, float eps,
+                                                       int D, __nv_bfloat16* __restrict__ out_bf16,
                                                        float* __restrict__ out_f32) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_part[8];
   const int b = blockIdx.x, tid = threadIdx.x;
-  const float* row = x + (long long)b * D;
+  float* row = x + (long long)b * D;
   float ss = 0.f;
   for (int c = tid * 4; c < D; c += blockDim.x * 4) {
     float4 v = *reinterpret_cast<const float4*>(row + c);
+    if (S > 0) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int sp = 0; sp < S; ++sp) {
+        const float4 q = __ldcg(reinterpret_cast<const float4*>(partials + sp * part_stride + (long long)b * D + c));
+        acc.x += q.x, acc.y += q.y, acc.z += q.z, acc.w += q.w;
+      }
+      v.x += acc.x, v.y += acc.y, v.z += acc.z, v.w += acc.w;
+      *reinterpret_cast<float4*>(row + c) = v;
+    }
     ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   ss = warp_sum(ss);
@@ -74,7 +90,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
   for (int w = 0; w < 8; ++w) tot += s_part[w];
   const float r = rsqrtf(tot / (float)D + eps);
   for (int c = tid * 4; c < D; c += blockDim.x * 4) {
-    float4 v = *reinterpret_cast<const float4*>(row + c);
+    float4 v = *reinterpret_cast<const float4*>(row + c);      // this thread's own stores above
     float4 a = *reinterpret_cast<const float4*>(alpha + c);
     float4 o = make_float4(v.x * r * a.x, v.y * r * a.y, v.z * r * a.z, v.w * r * a.w);
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + (long long)b * D + c) = o;
@@ -88,33 +104,47 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
   }
 }
 
-void launch_rmsnorm(const float* x, const float* alpha, float eps, int B, int D, __nv_bfloat16* out_bf16,
+void launch_rmsnorm(float* x, const PartialSums& ps, const float* alpha, float eps, int B, int D, __nv_bfloat16* out_bf16,
                     float* out_f32, cudaStream_t st) {
   DSM_CHECK(D % 4 == 0, DSM_ERR_UNSUPPORTED, "rmsnorm: D=%d", D);
-  rmsnorm_kernel<<<B, 256, 0, st>>>(x, alpha, eps, D, out_bf16, out_f32);
+  launch_k(rmsnorm_kernel, B, 256, 0, st, x, ps.planes, ps.count, ps.stride, alpha, eps, D, out_bf16, out_f32);
   check_launch("rmsnorm");
 }
 
 // ================================================================================================
 // RoPE in f32 (transformer.rs:372-378) on q, k; q -> bf16 [B, H*D]; k, v -> bf16 ring slot cur_index[b].
 // ================================================================================================
-__global__ void __launch_bounds__(256) rope_scatter_bf16_kernel(const float* __restrict__ qkv, RingState rs, int H,
+// The QKV projection may arrive as split-K partial planes [S][B][3*H*D] (S > 0): they are added here, in split order.
+__device__ __forceinline__ float2 load_qkv2(const float* __restrict__ qkv, int S, long long stride, long long off) {
+  if (S == 0) return *reinterpret_cast<const float2*>(qkv + off);
+  float2 a = make_float2(0.f, 0.f);
+  for (int sp = 0; sp < S; ++sp) {
+    const float2 v = __ldcg(reinterpret_cast<const float2*>(qkv + sp * stride + off));
+    a.x += v.x, a.y += v.y;
+  }
+  return a;
+}
+
+__global__ void __launch_bounds__(256) rope_scatter_bf16_kernel(const float* __restrict__ qkv, int S, long long part_stride,
+                                                                 RingState rs, int H,
                                                                  int D, int context, const float* __restrict__ inv_freq,
                                                                  __nv_bfloat16* __restrict__ q_out,
                                                                  __nv_bfloat16* __restrict__ k_ring,
                                                                  __nv_bfloat16* __restrict__ v_ring) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int slot = (int)rs.cur_index[b];
   const float pos = (float)rs.rope_pos[b];
   const int HD = H * D, half = D / 2;
-  const float* row = qkv + (long long)b * 3 * HD;
+  const long long row = (long long)b * 3 * HD;
   for (int i = threadIdx.x; i < H * half; i += blockDim.x) {
     const int h = i / half, p = i - h * half;
     float sn, cs;
     sincosf(pos * inv_freq[p], &sn, &cs);
-    const float2 q = *reinterpret_cast<const float2*>(row + h * D + 2 * p);
-    const float2 k = *reinterpret_cast<const float2*>(row + HD + h * D + 2 * p);
-    const float2 v = *reinterpret_cast<const float2*>(row + 2 * HD + h * D + 2 * p);
+    const float2 q = load_qkv2(qkv, S, part_stride, row + h * D + 2 * p);
+    const float2 k = load_qkv2(qkv, S, part_stride, row + HD + h * D + 2 * p);
+    const float2 v = load_qkv2(qkv, S, part_stride, row + 2 * HD + h * D + 2 * p);
     *reinterpret_cast<__nv_bfloat162*>(q_out + (long long)b * HD + h * D + 2 * p) =
         __floats2bfloat162_rn(q.x * cs - q.y * sn, q.x * sn + q.y * cs);
     const long long o = (((long long)b * H + h) * context + slot) * D + 2 * p;
@@ -123,10 +153,11 @@ __global__ void __launch_bounds__(256) rope_scatter_bf16_kernel(const float* __r
   }
 }
 
-void launch_rope_scatter_bf16(const float* qkv, const RingState& rs, int B, int H, int D, int context,
+void launch_rope_scatter_bf16(const float* qkv, const PartialSums& ps, const RingState& rs, int B, int H, int D, int context,
                               const float* inv_freq, __nv_bfloat16* q_out, __nv_bfloat16* k_ring,
                               __nv_bfloat16* v_ring, cudaStream_t st) {
-  rope_scatter_bf16_kernel<<<B, 256, 0, st>>>(qkv, rs, H, D, context, inv_freq, q_out, k_ring, v_ring);
+  launch_k(rope_scatter_bf16_kernel, B, 256, 0, st, ps.count ? ps.planes : qkv, ps.count, ps.stride, rs, H, D, context, inv_freq,
+           q_out, k_ring, v_ring);
   check_launch("rope_scatter_bf16");
 }
 
@@ -147,53 +178,32 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
                : "l"(p));
   return r;
 }
-// Same, with an L2 evict-first policy: 25 GB of KV rings stream through the 126 MB L2 every step and would
-// otherwise evict the codec's weights and activations that the concurrent Mimi branch re-reads.
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ uint4 ld_stream16(const void* p, uint64_t pol) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p), "l"(pol));
-  return r;
-}
-
-// GROUPS independent 128-thread groups per CTA, each walking its own (stream, head) items (named barriers), so
-// that a persistent one-CTA-per-SM grid still overlaps the phases of two items.
-template <int D, int UNROLL, bool EVICT, int GROUPS>
-__global__ void __launch_bounds__(128 * GROUPS, GROUPS == 1 ? 8 : 3) lm_attention_kernel(const __nv_bfloat16* __restrict__ q, RingState rs,
-                                                            const uint8_t* __restrict__ mask, int H, int context,
-                                                            int n_items, const __nv_bfloat16* __restrict__ k_ring,
-                                                            const __nv_bfloat16* __restrict__ v_ring,
-                                                            __nv_bfloat16* __restrict__ out) {
+template <int D, int UNROLL>
+__global__ void __launch_bounds__(128, 8) lm_attention_kernel(const __nv_bfloat16* __restrict__ q, RingState rs,
+                                                               const uint8_t* __restrict__ mask, int H, int context,
+                                                               const __nv_bfloat16* __restrict__ k_ring,
+                                                               const __nv_bfloat16* __restrict__ v_ring,
+                                                               __nv_bfloat16* __restrict__ out) {
   constexpr int LPK = D / 8;          // lanes per key
   constexpr int KPW = 32 / LPK;       // keys per warp-load
   constexpr int NW = 4;
   extern __shared__ float sm[];
-  const int grp = threadIdx.x / 128;
-  const int gsz = context > 4 * D ? context : 4 * D;   // floats of one group's buffer
-  float* sc = sm + grp * gsz;         // [context] scores, then reused as [NW][D] partial outputs
+  float* sc = sm;                     // [context] scores, then reused as [NW][D] partial outputs
   float* red = sc;
-  __shared__ float s_red_all[GROUPS][NW];
-  float* s_red = s_red_all[grp];
-  const int tid = threadIdx.x % 128, warp = tid / 32, lane = tid % 32;
-  auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
+  __shared__ float s_red[NW];
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  auto group_sync = [&]() { __syncthreads(); };
   const int HD = H * D;
-  const uint64_t pol = EVICT ? l2_evict_first_policy() : 0;
-  // grid == n_items: one (stream, head) per CTA.  A smaller grid walks the items (persistent form: every
-  // CTA is resident at once, so a co-scheduled kernel with large CTAs is never starved of SM space).
-  for (int item = blockIdx.x * GROUPS + grp; item < n_items; item += gridDim.x * GROUPS) {
-  const int b = item / H, h = item % H;
+  pdl_launch_dependents();
+  pdl_wait();
+  {
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
   __nv_bfloat16* orow = out + (long long)b * HD + h * D;
   const bool active = mask ? mask[b] != 0 : true;
   if (!active) {
     // an inactive stream's output is never consumed (asr.rs:221-223); skip the ring read
     for (int d = tid; d < D; d += 128) orow[d] = __float2bfloat16_rn(0.f);
-    continue;
+    return;
   }
   const int n = ring_visible_count(rs.cur_pos[b], context);             // visible slots are [0, n)
   const int c8 = lane % LPK, sub = lane / LPK;
@@ -214,7 +224,7 @@ __global__ void __launch_bounds__(128 * GROUPS, GROUPS == 1 ? 8 : 3) lm_attentio
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       const int j = j0 + u * KPW + sub;
-      kv[u] = j < n ? (EVICT ? ld_stream16(kb + (long long)j * D + c8 * 8, pol) : ld_stream16(kb + (long long)j * D + c8 * 8)) : make_uint4(0, 0, 0, 0);
+      kv[u] = j < n ? ld_stream16(kb + (long long)j * D + c8 * 8) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(128 * GROUPS, GROUPS == 1 ? 8 : 3) lm_attentio
     for (int u = 0; u < UNROLL; ++u) {
       const int j = j0 + u * KPW + sub;
       const bool ok = j < n;
-      vv[u] = ok ? (EVICT ? ld_stream16(vb + (long long)j * D + c8 * 8, pol) : ld_stream16(vb + (long long)j * D + c8 * 8)) : make_uint4(0, 0, 0, 0);
+      vv[u] = ok ? ld_stream16(vb + (long long)j * D + c8 * 8) : make_uint4(0, 0, 0, 0);
       pj[u] = ok ? sc[j] : 0.f;
     }
 #pragma unroll
@@ -295,47 +305,16 @@ __global__ void __launch_bounds__(128 * GROUPS, GROUPS == 1 ? 8 : 3) lm_attentio
     const float v = (red[d] + red[D + d] + red[2 * D + d] + red[3 * D + d]) * inv;
     orow[d] = __float2bfloat16_rn(v);
   }
-  group_sync();                    // red[] is the next item's score buffer
   }
 }
 
 void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint8_t* mask, int B, int H, int D,
                          int context, const __nv_bfloat16* k_ring, const __nv_bfloat16* v_ring, __nv_bfloat16* out,
                          cudaStream_t st) {
-  size_t smem = (size_t)std::max(context, 4 * D) * sizeof(float);
-  // DSM_ATTN_CARVEOUT=1: request the maximum shared-memory carve-out so attention CTAs can share an SM
-  // with the codec's tensor-core GEMMs (an SM only hosts kernels that agree on the carve-out)
-  static bool carveout_set = false;
-  if (!carveout_set) {
-    const char* e = getenv("DSM_ATTN_CARVEOUT");
-    if (e && e[0] == '1') {
-      DSM_CUDA(cudaFuncSetAttribute(lm_attention_kernel<128, 8, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    cudaSharedmemCarveoutMaxShared));
-      DSM_CUDA(cudaFuncSetAttribute(lm_attention_kernel<64, 8, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    cudaSharedmemCarveoutMaxShared));
-    }
-    carveout_set = true;
-  }
-  static const int max_ctas = [] { const char* e = getenv("DSM_ATTN_CTAS"); return e ? atoi(e) : 0; }();
-  static const int evict = [] { const char* e = getenv("DSM_ATTN_EVICT_FIRST"); return e ? atoi(e) : 0; }();
-  // DSM_ATTN_FAT=n: persistent grid of n CTAs of 2 x 128 threads with 12 loads in flight per thread (experiment:
-  // a footprint that leaves most of an SM to a co-resident codec GEMM CTA)
-  static const int fat = [] { const char* e = getenv("DSM_ATTN_FAT"); return e ? atoi(e) : 0; }();
-  const int items = B * H;
-  const int grid = max_ctas > 0 ? std::min(items, max_ctas) : items;
-  if (fat > 0 && D == 128) {
-    lm_attention_kernel<128, 12, false, 2><<<std::min(fat, (items + 1) / 2), 256, 2 * smem, st>>>(q, rs, mask, H, context, items, k_ring,
-                                                                                                 v_ring, out);
-  } else if (D == 128 && evict)
-    lm_attention_kernel<128, 8, true, 1><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
-  else if (D == 128)
-    lm_attention_kernel<128, 8, false, 1><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
-  else if (D == 64 && evict)
-    lm_attention_kernel<64, 8, true, 1><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
-  else if (D == 64)
-    lm_attention_kernel<64, 8, false, 1><<<grid, 128, smem, st>>>(q, rs, mask, H, context, items, k_ring, v_ring, out);
-  else
-    fail(DSM_ERR_UNSUPPORTED, "lm_attention: head_dim %d (64 or 128)", D);
+  const size_t smem = (size_t)std::max(context, 4 * D) * sizeof(float);
+  if (D == 128) launch_k(lm_attention_kernel<128, 8>, B * H, 128, smem, st, q, rs, mask, H, context, k_ring, v_ring, out);
+  else if (D == 64) launch_k(lm_attention_kernel<64, 8>, B * H, 128, smem, st, q, rs, mask, H, context, k_ring, v_ring, out);
+  else fail(DSM_ERR_UNSUPPORTED, "lm_attention: head_dim %d (64 or 128)", D);
   check_launch("lm_attention");
 }
 
@@ -352,17 +331,20 @@ void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint
 // The query and the probabilities are split into two int8 terms (x ~ s * (x1 + x2 / 254), 15 bits), so the only
 // rounding that matters is the ring's own 8 bits.
 // ================================================================================================
-__global__ void __launch_bounds__(256) rope_scatter_q8_kernel(const float* __restrict__ qkv, RingState rs, int H, int D,
+__global__ void __launch_bounds__(256) rope_scatter_q8_kernel(const float* __restrict__ qkv, int S, long long part_stride,
+                                                               RingState rs, int H, int D,
                                                                int context, int ctxp, const float* __restrict__ inv_freq,
                                                                __nv_bfloat16* __restrict__ q_out, int8_t* __restrict__ k_ring,
                                                                int8_t* __restrict__ v_ring, float* __restrict__ k_scale,
                                                                float* __restrict__ v_scale,
                                                                __nv_bfloat16* __restrict__ v_ring_bf16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int slot = (int)rs.cur_index[b];
   const float pos = (float)rs.rope_pos[b];
   const int HD = H * D, half = D / 2;
-  const float* row = qkv + (long long)b * 3 * HD;
+  const long long row = (long long)b * 3 * HD;
   for (int h = warp; h < H; h += blockDim.x / 32) {
     // a lane owns the pairs p = lane, lane + 32 (D = 128) or p = lane (D = 64)
     float kr[4], vr[4];
@@ -374,9 +356,9 @@ __global__ void __launch_bounds__(256) rope_scatter_q8_kernel(const float* __res
       if (p >= half) continue;
       float sn, cs;
       sincosf(pos * inv_freq[p], &sn, &cs);
-      const float2 q = *reinterpret_cast<const float2*>(row + h * D + 2 * p);
-      const float2 k = *reinterpret_cast<const float2*>(row + HD + h * D + 2 * p);
-      const float2 v = *reinterpret_cast<const float2*>(row + 2 * HD + h * D + 2 * p);
+      const float2 q = load_qkv2(qkv, S, part_stride, row + h * D + 2 * p);
+      const float2 k = load_qkv2(qkv, S, part_stride, row + HD + h * D + 2 * p);
+      const float2 v = load_qkv2(qkv, S, part_stride, row + 2 * HD + h * D + 2 * p);
       *reinterpret_cast<__nv_bfloat162*>(q_out + (long long)b * HD + h * D + 2 * p) =
           __floats2bfloat162_rn(q.x * cs - q.y * sn, q.x * sn + q.y * cs);
       kr[2 * i] = k.x * cs - k.y * sn, kr[2 * i + 1] = k.x * sn + k.y * cs;
@@ -410,10 +392,10 @@ __global__ void __launch_bounds__(256) rope_scatter_q8_kernel(const float* __res
   }
 }
 
-void launch_rope_scatter_q8(const float* qkv, const RingState& rs, int B, int H, int D, int context, const float* inv_freq,
-                            __nv_bfloat16* q_out, const KvRingQ8& r, cudaStream_t st) {
+void launch_rope_scatter_q8(const float* qkv, const PartialSums& ps, const RingState& rs, int B, int H, int D, int context,
+                            const float* inv_freq, __nv_bfloat16* q_out, const KvRingQ8& r, cudaStream_t st) {
   DSM_CHECK(D == 64 || D == 128, DSM_ERR_UNSUPPORTED, "rope_scatter_q8: head_dim %d (64 or 128)", D);
-  rope_scatter_q8_kernel<<<B, 256, 0, st>>>(qkv, rs, H, D, context, r.ctxp, inv_freq, q_out, r.k, r.v, r.k_scale, r.v_scale,
+  launch_k(rope_scatter_q8_kernel, B, 256, 0, st, ps.count ? ps.planes : qkv, ps.count, ps.stride, rs, H, D, context, r.ctxp, inv_freq, q_out, r.k, r.v, r.k_scale, r.v_scale,
                                             r.v_bf16);
   check_launch("rope_scatter_q8");
 }
@@ -440,6 +422,8 @@ __global__ void __launch_bounds__(128, 8) lm_attention_q8_kernel(const __nv_bflo
                                                                   const float* __restrict__ v_scale,
                                                                   const __nv_bfloat16* __restrict__ v_ring_bf16,
                                                                   __nv_bfloat16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int LPK = D / 16;         // lanes per key row
   constexpr int KPW = 32 / LPK;       // keys per warp-load
   constexpr int LPB = D / 4;          // lanes per key-quad block
@@ -655,10 +639,10 @@ void launch_lm_attention_q8(const __nv_bfloat16* q, const RingState& rs, const u
   const size_t smem = lm_attention_q8_smem(D, r.ctxp);
   DSM_CHECK(smem <= 48 * 1024, DSM_ERR_UNSUPPORTED, "lm_attention_q8: context %d needs %zu bytes of shared memory", context, smem);
 #define Q8_ARGS q, rs, mask, H, context, r.ctxp, r.k, r.v, r.k_scale, r.v_scale, r.v_bf16, out
-  if (D == 128 && !r.v_bf16) lm_attention_q8_kernel<128, 8, true><<<B * H, 128, smem, st>>>(Q8_ARGS);
-  else if (D == 128) lm_attention_q8_kernel<128, 8, false><<<B * H, 128, smem, st>>>(Q8_ARGS);
-  else if (D == 64 && !r.v_bf16) lm_attention_q8_kernel<64, 8, true><<<B * H, 128, smem, st>>>(Q8_ARGS);
-  else if (D == 64) lm_attention_q8_kernel<64, 8, false><<<B * H, 128, smem, st>>>(Q8_ARGS);
+  if (D == 128 && !r.v_bf16) launch_k(lm_attention_q8_kernel<128, 8, true>, B * H, 128, smem, st, Q8_ARGS);
+  else if (D == 128) launch_k(lm_attention_q8_kernel<128, 8, false>, B * H, 128, smem, st, Q8_ARGS);
+  else if (D == 64 && !r.v_bf16) launch_k(lm_attention_q8_kernel<64, 8, true>, B * H, 128, smem, st, Q8_ARGS);
+  else if (D == 64) launch_k(lm_attention_q8_kernel<64, 8, false>, B * H, 128, smem, st, Q8_ARGS);
 #undef Q8_ARGS
   else
     fail(DSM_ERR_UNSUPPORTED, "lm_attention_q8: head_dim %d (64 or 128)", D);
@@ -669,6 +653,8 @@ void launch_lm_attention_q8(const __nv_bfloat16* q, const RingState& rs, const u
 // SiLU gate (batched_transformer.rs:170-176): contiguous halves, gate first.
 // ================================================================================================
 __global__ void silu_gate_kernel(const float* __restrict__ h, int Hd, __nv_bfloat16* __restrict__ g, long long total4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int per_row = Hd / 4;
@@ -686,22 +672,34 @@ __global__ void silu_gate_kernel(const float* __restrict__ h, int Hd, __nv_bfloa
 void launch_silu_gate(const float* h, int B, int Hd, __nv_bfloat16* g, cudaStream_t st) {
   DSM_CHECK(Hd % 4 == 0, DSM_ERR_UNSUPPORTED, "silu_gate: hidden=%d", Hd);
   const long long total4 = (long long)B * Hd / 4;
-  silu_gate_kernel<<<(unsigned)ceil_div(total4, 256LL), 256, 0, st>>>(h, Hd, g, total4);
+  launch_k(silu_gate_kernel, (unsigned)ceil_div(total4, 256LL), 256, 0, st, h, Hd, g, total4);
   check_launch("silu_gate");
 }
 
 // ================================================================================================
 // greedy argmax over the text logits (asr.rs:208-210), first index on ties.
 // ================================================================================================
-__global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ logits, int V, uint32_t* __restrict__ tokens) {
+// The text head may arrive as split-K partial planes [S][B][V]: they are added here in split order and the finished
+// logits are written out (they are an output of LmModel::forward).
+__global__ void __launch_bounds__(256) argmax_kernel(float* __restrict__ logits, const float* __restrict__ partials, int S,
+                                                      long long part_stride, int V, uint32_t* __restrict__ tokens) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_val[8];
   __shared__ int s_idx[8];
   const int b = blockIdx.x, tid = threadIdx.x;
-  const float* row = logits + (long long)b * V;
+  float* row = logits + (long long)b * V;
   float best = -INFINITY;
   int bi = 0x7fffffff;
   for (int j = tid; j < V; j += blockDim.x) {
-    const float v = row[j];
+    float v;
+    if (S > 0) {
+      v = 0.f;
+      for (int sp = 0; sp < S; ++sp) v += __ldcg(partials + sp * part_stride + (long long)b * V + j);
+      row[j] = v;
+    } else {
+      v = row[j];
+    }
     if (v > best) best = v, bi = j;
   }
 #pragma unroll
@@ -719,8 +717,8 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ l
     tokens[b] = (bi < 0 || bi >= V) ? 0u : (uint32_t)bi;
   }
 }
-void launch_argmax(const float* logits, int B, int V, uint32_t* tokens, cudaStream_t st) {
-  argmax_kernel<<<B, 256, 0, st>>>(logits, V, tokens);
+void launch_argmax(float* logits, const PartialSums& ps, int B, int V, uint32_t* tokens, cudaStream_t st) {
+  launch_k(argmax_kernel, B, 256, 0, st, logits, ps.planes, ps.count, ps.stride, V, tokens);
   check_launch("argmax");
 }
 
@@ -731,6 +729,8 @@ void launch_argmax(const float* logits, int B, int V, uint32_t* tokens, cudaStre
 __global__ void __launch_bounds__(256) extra_heads_kernel(const __nv_bfloat16* __restrict__ ys,
                                                            const __nv_bfloat16* __restrict__ w, int nh, int dim, int B,
                                                            int D, float* __restrict__ prs) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_logit[];  // [nh*dim]
   const int b = blockIdx.x, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const __nv_bfloat16* y = ys + (long long)b * D;
@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(256) extra_heads_kernel(const __nv_bfloat16* _
 void launch_extra_heads(const __nv_bfloat16* ys, const __nv_bfloat16* w, int nh, int dim, int B, int D, float* prs,
                         cudaStream_t st) {
   DSM_CHECK(D % 256 == 0 && nh <= 256, DSM_ERR_UNSUPPORTED, "extra_heads: D=%d nh=%d", D, nh);
-  extra_heads_kernel<<<B, 256, nh * dim * sizeof(float), st>>>(ys, w, nh, dim, B, D, prs);
+  launch_k(extra_heads_kernel, B, 256, nh * dim * sizeof(float), st, ys, w, nh, dim, B, D, prs);
   check_launch("extra_heads");
 }
 
@@ -772,6 +772,8 @@ void launch_extra_heads(const __nv_bfloat16* ys, const __nv_bfloat16* w, int nh,
 __global__ void asr_prepare_kernel(const uint32_t* __restrict__ next_cb, const uint8_t* __restrict__ first_step,
                                    const uint32_t* __restrict__ text_tok, uint32_t pad, uint32_t start, int B, int n_cb,
                                    uint32_t* __restrict__ lm_audio_in, uint32_t* __restrict__ lm_text_in) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * n_cb) return;
   const int b = i / n_cb;
@@ -781,7 +783,7 @@ __global__ void asr_prepare_kernel(const uint32_t* __restrict__ next_cb, const u
 }
 void launch_asr_prepare(const uint32_t* next_cb, const uint8_t* first_step, const uint32_t* text_tok, uint32_t pad,
                         uint32_t start, int B, int n_cb, uint32_t* lm_audio_in, uint32_t* lm_text_in, cudaStream_t st) {
-  asr_prepare_kernel<<<ceil_div(B * n_cb, 256), 256, 0, st>>>(next_cb, first_step, text_tok, pad, start, B, n_cb,
+  launch_k(asr_prepare_kernel, ceil_div(B * n_cb, 256), 256, 0, st, next_cb, first_step, text_tok, pad, start, B, n_cb,
                                                              lm_audio_in, lm_text_in);
   check_launch("asr_prepare");
 }
@@ -789,6 +791,8 @@ void launch_asr_prepare(const uint32_t* next_cb, const uint8_t* first_step, cons
 __global__ void asr_commit_kernel(const uint32_t* __restrict__ codes, const uint8_t* __restrict__ mask,
                                   const uint32_t* __restrict__ sampled, int B, int n_cb, uint32_t* __restrict__ next_cb,
                                   uint32_t* __restrict__ text_tok, uint8_t* __restrict__ first_step) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * n_cb) return;
   const int b = i / n_cb;
@@ -801,7 +805,7 @@ __global__ void asr_commit_kernel(const uint32_t* __restrict__ codes, const uint
 }
 void launch_asr_commit(const uint32_t* codes, const uint8_t* mask, const uint32_t* sampled, int B, int n_cb,
                        uint32_t* next_cb, uint32_t* text_tok, uint8_t* first_step, cudaStream_t st) {
-  asr_commit_kernel<<<ceil_div(B * n_cb, 256), 256, 0, st>>>(codes, mask, sampled, B, n_cb, next_cb, text_tok, first_step);
+  launch_k(asr_commit_kernel, ceil_div(B * n_cb, 256), 256, 0, st, codes, mask, sampled, B, n_cb, next_cb, text_tok, first_step);
   check_launch("asr_commit");
 }
 

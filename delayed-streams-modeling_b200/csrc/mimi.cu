@@ -395,12 +395,7 @@ MimiImpl::MimiImpl(const dsm_mimi_spec& sp, const dsm_weights* w, int dev, int b
             "mimi spec outside the v0_1 family (n_q=%d qdim=%d dim=%d)", sp.n_q, sp.qdim, sp.dim);
   DSM_CHECK(sp.with_encoder || sp.with_decoder, DSM_ERR_INVALID_ARG, "mimi spec enables neither encoder nor decoder");
   DSM_CUDA(cudaSetDevice(device));
-  {
-    const char* e = getenv("DSM_MIMI_PRIORITY");
-    int lo = 0, hi = 0;
-    DSM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    DSM_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, (e && e[0] == '1') ? hi : 0));
-  }
+  DSM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   WeightTable wt(w);
   const bool random = (w == nullptr);
   // Tensor getter: from the table (either of `a|b` alternative names), or seeded host-side random init
@@ -490,7 +485,6 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
 
   SeanetBuild sb{this, &arena, B, &get, &wt, &enc_plan, &enc_commits};
   build_seanet(sb, L, DSM_FRAME_SIZE, nullptr, x, x_map, d_pcm, enc_state0, nullptr);
-  enc_seanet_end = enc_plan.size();
 
   const int Bc = B;
   const size_t row_bytes = (size_t)D * sizeof(float);

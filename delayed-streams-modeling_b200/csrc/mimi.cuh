@@ -90,7 +90,6 @@ struct MimiImpl {
   CommitEntry *d_enc_commits = nullptr, *d_dec_commits = nullptr;
   int enc_max_count = 0, dec_max_count = 0;
   Plan enc_plan, dec_plan;
-  size_t enc_seanet_end = 0;   // enc_plan[0, enc_seanet_end) is the SEANet encoder (the kernels that fill every SM)
   GraphExec enc_graph, dec_graph;
 
   // ---- decoder ----

@@ -9,6 +9,8 @@ namespace dsm {
 // ring bookkeeping -- kv_cache.rs:119-237 on the device, any t, no host sync
 // ================================================================================================
 __global__ void ring_advance_kernel(RingState rs, const uint8_t* __restrict__ mask, int B, int t, int context) {
+  pdl_launch_dependents();
+  pdl_wait();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const bool active = mask ? mask[b] != 0 : true;
@@ -26,7 +28,7 @@ __global__ void ring_advance_kernel(RingState rs, const uint8_t* __restrict__ ma
 }
 
 void launch_ring_advance(const RingState& rs, const uint8_t* mask, int B, int t, int context, cudaStream_t st) {
-  ring_advance_kernel<<<ceil_div(B, 128), 128, 0, st>>>(rs, mask, B, t, context);
+  launch_k(ring_advance_kernel, ceil_div(B, 128), 128, 0, st, rs, mask, B, t, context);
   check_launch("ring_advance");
 }
 
@@ -34,6 +36,8 @@ void launch_ring_advance(const RingState& rs, const uint8_t* mask, int B, int t,
 // LM kernels' fast-path rule, t > 1 the general one of the codec kernel.
 __global__ void ring_debug_kernel(RingState rs, const uint8_t* __restrict__ mask, int t, int context,
                                   uint32_t* __restrict__ indices, float* __restrict__ amask) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const bool active = mask ? mask[b] != 0 : true;
   const int i0 = (int)rs.cur_index[b];
@@ -50,7 +54,7 @@ __global__ void ring_debug_kernel(RingState rs, const uint8_t* __restrict__ mask
 }
 void launch_ring_debug(const RingState& rs, const uint8_t* mask, int B, int t, int context, uint32_t* indices, float* amask,
                        cudaStream_t st) {
-  ring_debug_kernel<<<B, 128, 0, st>>>(rs, mask, t, context, indices, amask);
+  launch_k(ring_debug_kernel, B, 128, 0, st, rs, mask, t, context, indices, amask);
   check_launch("ring_debug");
 }
 
@@ -66,6 +70,8 @@ __global__ void __launch_bounds__(256) init_conv_kernel(const float* __restrict_
                                                          const float* __restrict__ bias, int T, int C, int k,
                                                          float* __restrict__ out_raw, RowMap raw_map,
                                                          float* __restrict__ out_act, RowMap act_map) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* sw = sm;                 // [C][k]
   float* sx = sm + C * k;         // [tile_t + k - 1]
@@ -121,7 +127,7 @@ void launch_init_conv(const float* pcm, const float* state, int S, const float* 
   const int tile_t = 256 / (C / 4) * IC_R;
   dim3 grid(ceil_div(T, tile_t), B);
   size_t smem = (size_t)(C * k + tile_t + k - 1) * sizeof(float);
-  init_conv_kernel<8><<<grid, 256, smem, st>>>(pcm, state, S, w, bias, T, C, k, out_raw, raw_map, out_act, act_map);
+  launch_k(init_conv_kernel<8>, grid, 256, smem, st, pcm, state, S, w, bias, T, C, k, out_raw, raw_map, out_act, act_map);
   check_launch("init_conv");
 }
 
@@ -132,6 +138,8 @@ void launch_init_conv(const float* pcm, const float* state, int S, const float* 
 __global__ void __launch_bounds__(256) final_conv_kernel(const float* __restrict__ x, RowMap x_map,
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           int B, int T, int KC, float* __restrict__ pcm) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sw[];
   for (int i = threadIdx.x; i < KC; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -155,7 +163,7 @@ void launch_final_conv(const float* x, RowMap x_map, const float* w, const float
                        float* pcm, cudaStream_t st) {
   const int KC = k * C;
   DSM_CHECK(KC % 4 == 0, DSM_ERR_UNSUPPORTED, "final_conv: k*C=%d", KC);
-  final_conv_kernel<<<ceil_div(B * T, 8), 256, KC * sizeof(float), st>>>(x, x_map, w, bias, B, T, KC, pcm);
+  launch_k(final_conv_kernel, ceil_div(B * T, 8), 256, KC * sizeof(float), st, x, x_map, w, bias, B, T, KC, pcm);
   check_launch("final_conv");
 }
 
@@ -166,6 +174,8 @@ void launch_final_conv(const float* x, RowMap x_map, const float* w, const float
 // (source and destination ranges overlap: the state shifts by T rows) is still copied correctly.
 __global__ void __launch_bounds__(256) commit_state_kernel(const CommitEntry* __restrict__ entries,
                                                             const uint8_t* __restrict__ mask, int* first_step_flag) {
+  pdl_launch_dependents();
+  pdl_wait();
   const CommitEntry e = entries[blockIdx.x];
   const int b = blockIdx.y;
   const bool active = mask ? mask[b] != 0 : true;
@@ -189,37 +199,45 @@ __global__ void __launch_bounds__(256) commit_state_kernel(const CommitEntry* __
     for (int i = threadIdx.x; i < e.count; i += blockDim.x) dst[i] = 0.f;
   }
 }
-__global__ void clear_flag_kernel(int* flag) { *flag = 0; }
+__global__ void clear_flag_kernel(int* flag) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *flag = 0;
+}
 
 void launch_commit_state(const CommitEntry* entries_dev, int n_entries, int max_count, const uint8_t* mask,
                          int* first_step_flag, int B, cudaStream_t st) {
   DSM_CHECK(max_count <= 4096, DSM_ERR_UNSUPPORTED, "commit_state: %d floats per entry (max 4096)", max_count);
-  commit_state_kernel<<<dim3(n_entries, B), 256, 0, st>>>(entries_dev, mask, first_step_flag);
+  launch_k(commit_state_kernel, dim3(n_entries, B), 256, 0, st, entries_dev, mask, first_step_flag);
   check_launch("commit_state");
   if (first_step_flag) {
-    clear_flag_kernel<<<1, 1, 0, st>>>(first_step_flag);
+    launch_k(clear_flag_kernel, 1, 1, 0, st, first_step_flag);
     check_launch("clear_flag");
   }
 }
 
 __global__ void replicate_pad_kernel(float* x, long long stride_b, int S, int C, const int* first_step_flag) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (!*first_step_flag) return;
   float* base = x + (long long)blockIdx.x * stride_b;
   for (int i = threadIdx.x; i < S * C; i += blockDim.x) base[i] = base[S * C + (i % C)];
 }
 void launch_replicate_pad(float* x, long long stride_b, int S, int C, const int* first_step_flag, int B,
                           cudaStream_t st) {
-  replicate_pad_kernel<<<B, 256, 0, st>>>(x, stride_b, S, C, first_step_flag);
+  launch_k(replicate_pad_kernel, B, 256, 0, st, x, stride_b, S, C, first_step_flag);
   check_launch("replicate_pad");
 }
 
 __global__ void zero_rows_kernel(const CommitEntry* __restrict__ entries, int b0) {
+  pdl_launch_dependents();
+  pdl_wait();
   const CommitEntry e = entries[blockIdx.x];
   float* dst = e.dst + (long long)(b0 + blockIdx.y) * e.dst_stride_b;
   for (int i = threadIdx.x; i < e.count; i += blockDim.x) dst[i] = 0.f;
 }
 void launch_zero_rows(const CommitEntry* entries_dev, int n_entries, int b0, int nb, cudaStream_t st) {
-  zero_rows_kernel<<<dim3(n_entries, nb), 256, 0, st>>>(entries_dev, b0);
+  launch_k(zero_rows_kernel, dim3(n_entries, nb), 256, 0, st, entries_dev, b0);
   check_launch("zero_rows");
 }
 
@@ -232,6 +250,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                          const float* __restrict__ w, const float* __restrict__ bias,
                                                          float eps, int M, float* __restrict__ out,
                                                          __nv_bfloat16* __restrict__ planes, long long plane_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int V = D / 128;  // float4 per lane
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int m = blockIdx.x * (blockDim.x / 32) + warp;
@@ -271,7 +291,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 void launch_layernorm(const float* x, RowMap x_map, const float* w, const float* b, float eps, int M, int D,
                       float* out, cudaStream_t st, __nv_bfloat16* planes, long long plane_stride) {
   DSM_CHECK(D == 512, DSM_ERR_UNSUPPORTED, "layernorm: D=%d (only 512)", D);
-  layernorm_kernel<512><<<ceil_div(M, 8), 256, 0, st>>>(x, x_map, w, b, eps, M, out, planes, plane_stride);
+  launch_k(layernorm_kernel<512>, ceil_div(M, 8), 256, 0, st, x, x_map, w, b, eps, M, out, planes, plane_stride);
   check_launch("layernorm");
 }
 
@@ -284,6 +304,8 @@ __global__ void __launch_bounds__(256) rope_scatter_f32_kernel(float* __restrict
                                                                 int context, const float* __restrict__ inv_freq,
                                                                 float* __restrict__ k_ring,
                                                                 float* __restrict__ v_ring) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x;
   const int b = m / t, s = m - b * t;
   const bool active = mask ? mask[b] != 0 : true;
@@ -311,7 +333,7 @@ __global__ void __launch_bounds__(256) rope_scatter_f32_kernel(float* __restrict
 
 void launch_rope_scatter_f32(float* qkv, const RingState& rs, const uint8_t* mask, int B, int t, int H, int D,
                              int context, const float* inv_freq, float* k_ring, float* v_ring, cudaStream_t st) {
-  rope_scatter_f32_kernel<<<B * t, 256, 0, st>>>(qkv, rs, mask, t, H, D, context, inv_freq, k_ring, v_ring);
+  launch_k(rope_scatter_f32_kernel, B * t, 256, 0, st, qkv, rs, mask, t, H, D, context, inv_freq, k_ring, v_ring);
   check_launch("rope_scatter_f32");
 }
 
@@ -327,6 +349,8 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
                                                                const float* __restrict__ v_ring,
                                                                float* __restrict__ out,
                                                                __nv_bfloat16* __restrict__ planes, long long plane_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   static_assert(D == 64, "lane layout assumes 16 lanes x float4 per key");
   extern __shared__ float sm[];
   float* sc = sm;                       // [TQ][context]
@@ -470,7 +494,7 @@ void launch_codec_attention(const float* qkv, const RingState& rs, const uint8_t
                             __nv_bfloat16* planes, long long plane_stride) {
   DSM_CHECK(D == 64 && t <= 2, DSM_ERR_UNSUPPORTED, "codec_attention: D=%d t=%d", D, t);
   size_t smem = (size_t)(2 * context + 8 * 2 * D) * sizeof(float);
-  codec_attention_kernel<64, 2><<<B * H, 128, smem, st>>>(qkv, rs, mask, t, H, context, k_ring, v_ring, out, planes,
+  launch_k(codec_attention_kernel<64, 2>, B * H, 128, smem, st, qkv, rs, mask, t, H, context, k_ring, v_ring, out, planes,
                                                           plane_stride);
   check_launch("codec_attention");
 }
@@ -484,6 +508,8 @@ __global__ void __launch_bounds__(256) rvq_select_kernel(const float* __restrict
                                                           float* __restrict__ residual, long long res_stride,
                                                           uint32_t* __restrict__ codes, int n_q, int q,
                                                           __nv_bfloat16* __restrict__ planes, long long plane_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_val[8];
   __shared__ int s_idx[8];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -531,7 +557,7 @@ __global__ void __launch_bounds__(256) rvq_select_kernel(const float* __restrict
 void launch_rvq_select(const float* scores, int B, int bins, const float* embedding, int qdim, float* residual,
                        long long res_stride, uint32_t* codes, int n_q, int q, cudaStream_t st, __nv_bfloat16* planes,
                        long long plane_stride) {
-  rvq_select_kernel<<<B, 256, 0, st>>>(scores, bins, embedding, qdim, residual, res_stride, codes, n_q, q, planes,
+  launch_k(rvq_select_kernel, B, 256, 0, st, scores, bins, embedding, qdim, residual, res_stride, codes, n_q, q, planes,
                                        plane_stride);
   check_launch("rvq_select");
 }
@@ -539,6 +565,8 @@ void launch_rvq_select(const float* scores, int B, int bins, const float* embedd
 __global__ void __launch_bounds__(256) rvq_gather_sum_kernel(const uint32_t* __restrict__ codes, int n_q, int q0,
                                                               int q1, const float* __restrict__ embeddings, int bins,
                                                               int qdim, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   for (int d = threadIdx.x; d < qdim; d += blockDim.x) {
     float acc = 0.f;
@@ -553,7 +581,7 @@ __global__ void __launch_bounds__(256) rvq_gather_sum_kernel(const uint32_t* __r
 }
 void launch_rvq_gather_sum(const uint32_t* codes, int n_q, int q0, int q1, const float* embeddings, int bins, int qdim,
                            int B, float* out, cudaStream_t st) {
-  rvq_gather_sum_kernel<<<B, 256, 0, st>>>(codes, n_q, q0, q1, embeddings, bins, qdim, out);
+  launch_k(rvq_gather_sum_kernel, B, 256, 0, st, codes, n_q, q0, q1, embeddings, bins, qdim, out);
   check_launch("rvq_gather_sum");
 }
 
@@ -564,6 +592,8 @@ void launch_rvq_gather_sum(const uint32_t* codes, int n_q, int q0, int q1, const
 // ================================================================================================
 __global__ void upsample_dw_kernel(const float* __restrict__ x, const float* __restrict__ state,
                                    const float* __restrict__ w, int C, int s, float* __restrict__ out, RowMap out_map) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float xv = x[(long long)b * C + c], pv = state[(long long)b * C + c];
@@ -573,7 +603,7 @@ __global__ void upsample_dw_kernel(const float* __restrict__ x, const float* __r
 }
 void launch_upsample_dw(const float* x, const float* state, const float* w, int B, int C, int s, float* out,
                         RowMap out_map, cudaStream_t st) {
-  upsample_dw_kernel<<<B, 256, 0, st>>>(x, state, w, C, s, out, out_map);
+  launch_k(upsample_dw_kernel, B, 256, 0, st, x, state, w, C, s, out, out_map);
   check_launch("upsample_dw");
 }
 

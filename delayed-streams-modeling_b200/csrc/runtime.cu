@@ -221,6 +221,11 @@ void fill_u32(uint32_t* dst, size_t n, uint32_t v, cudaStream_t st) {
 // ---- CUDA graph -----------------------------------------------------------------------------------
 static int g_graphs_override = -1;   // -1: follow DSM_NO_GRAPH, 0/1: forced by dsm_set_graphs
 void set_graphs_enabled(int v) { g_graphs_override = v; }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("DSM_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 bool graphs_enabled() {
   if (g_graphs_override >= 0) return g_graphs_override != 0;
   const char* e = getenv("DSM_NO_GRAPH");

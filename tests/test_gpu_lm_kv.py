@@ -34,6 +34,7 @@ def wrapped_ring_run():
     worst = {k: 0.0 for k in BARS}
     worst_wrapped = {k: 0.0 for k in BARS}
     same = {k: 0 for k in BARS}
+    far = {k: 0 for k in BARS}          # token mismatches that are NOT near-ties of the oracle's logits
     for i in range(steps):
         audio = rng.integers(0, 2048, (b, spec.audio_codebooks))
         mask = None if i % 97 else np.array([1, 1, 0, 1], np.uint8)     # stream 2 sits a few steps out
@@ -41,27 +42,34 @@ def wrapped_ring_run():
                                [True] * b if mask is None else [bool(x) for x in mask])
         ol = ol[:, 0].numpy()
         act = np.ones(b, bool) if mask is None else mask.astype(bool)
+        o_tok = ol.argmax(-1)
         for k, g in gs.items():
             gl, _ = g.forward_cond(text, audio, None, mask, want_ys=False)
             e = rel_err(gl[act], ol[act])
             worst[k] = max(worst[k], e)
             if i >= spec.context:
                 worst_wrapped[k] = max(worst_wrapped[k], e)
-            same[k] += int((gl.argmax(-1)[act] == ol.argmax(-1)[act]).sum())
-        text = np.where(act, ol.argmax(-1), text)
+            g_tok = gl.argmax(-1)
+            same[k] += int((g_tok[act] == o_tok[act]).sum())
+            # a differing token must be one the oracle itself ranks within the logits tolerance of its argmax
+            gap = ol[np.arange(b), o_tok] - ol[np.arange(b), g_tok]
+            far[k] += int(((gap > BARS[k] * np.abs(ol).max()) & act).sum())
+        text = np.where(act, o_tok, text)
     total = steps * b - len(range(0, steps, 97))
     for k in BARS:
         print(f"kv {k:6s}: logits rel err max {worst[k]:.3e} (wrapped ring {worst_wrapped[k]:.3e}), "
-              f"greedy tokens identical {same[k]}/{total}")
-    return worst, same, total
+              f"greedy tokens identical {same[k]}/{total}, mismatches outside the tolerance {far[k]}")
+    return worst, same, far, total
 
 
 @pytest.mark.parametrize("kv", list(BARS))
 def test_full_wrapped_ring_against_oracle(wrapped_ring_run, kv):
-    worst, same, total = wrapped_ring_run
+    worst, same, far, total = wrapped_ring_run
     assert worst[kv] < BARS[kv], f"{kv}: logits rel err {worst[kv]:.3e}"
-    # random-init logits over 8000 entries are nearly flat: a handful of near-ties may resolve differently
-    assert same[kv] >= total - (3 if kv == "bf16" else 12), f"{kv}: tokens identical on {same[kv]}/{total}"
+    # Random-init logits over 8000 entries are nearly flat (top-2 gaps of 1e-3 of the range are common), so ~1 % of the
+    # greedy tokens are near-ties that bf16 operands resolve either way; none may differ by more than the tolerance.
+    assert far[kv] == 0, f"{kv}: {far[kv]} greedy tokens differ beyond the logits tolerance"
+    assert same[kv] >= 0.98 * total, f"{kv}: tokens identical on {same[kv]}/{total}"
 
 
 @pytest.mark.parametrize("kv", list(BARS))

@@ -22,6 +22,7 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--eager", action="store_true")
 ap.add_argument("--model", default="1b")
 ap.add_argument("--workload", default="asr", choices=["asr", "mimi", "decode", "lm"])
+ap.add_argument("--kv", default="bf16", choices=["bf16", "int8", "int8k"])
 a = ap.parse_args()
 if a.eager:
     api.set_graphs(False)
@@ -32,7 +33,7 @@ audio = synth_audio(min(B, 8), a.steps)
 audio = np.tile(audio, (B // audio.shape[0] + 1, 1))[:B]
 if a.workload == "asr":
     mimi = api.Mimi(mspec, None, B, decoder=False)
-    lm = api.LmModel(lspec, None, B)
+    lm = api.LmModel(lspec, None, B, kv_dtype=a.kv)
     asr = api.AsrState(mimi, lm)
     lm.debug_set_position(2000)
     for i in range(a.steps):
@@ -40,7 +41,7 @@ if a.workload == "asr":
         print("step", i, "ms", asr.last_step_ms())
 elif a.workload == "lm":
     import time
-    lm = api.LmModel(lspec, None, B)
+    lm = api.LmModel(lspec, None, B, kv_dtype=a.kv)
     asr = api.AsrState(None, lm)
     lm.debug_set_position(2000)
     codes = np.random.default_rng(7).integers(0, 2048, (B, 32)).astype(np.uint32)
@@ -48,6 +49,10 @@ elif a.workload == "lm":
         t0 = time.perf_counter()
         asr.step_tokens(codes, None, want_messages=False)
         print("lm step", i, "wall ms", (time.perf_counter() - t0) * 1e3, "device ms", asr.last_step_ms()[0])
+    t0 = time.perf_counter()
+    for i in range(50):
+        asr.step_tokens(codes, None, want_messages=False)
+    print("lm branch alone: %.3f ms/step over 50 steps" % ((time.perf_counter() - t0) * 1e3 / 50))
 elif a.workload == "mimi":
     import time
     import torch
@@ -60,6 +65,12 @@ elif a.workload == "mimi":
         mimi.encode_step(pcm[i], None, out=out)
         mimi.synchronize()
         print("mimi step", i, "wall ms", (time.perf_counter() - t0) * 1e3)
+    mimi.synchronize()
+    t0 = time.perf_counter()
+    for i in range(50):
+        mimi.encode_step(pcm[i % a.steps], None, out=out)
+    mimi.synchronize()
+    print("mimi branch alone: %.3f ms/step over 50 steps" % ((time.perf_counter() - t0) * 1e3 / 50))
 else:
     mimi = api.Mimi(mspec, None, B, encoder=False, decoder=True)
     codes = np.random.default_rng(7).integers(0, 2048, (B, 32)).astype(np.uint32)
