@@ -74,6 +74,16 @@ class WireOutC(C.Structure):
                 ("step_idx", C.c_int64), ("prs", C.POINTER(C.c_float)), ("n_prs", C.c_int32), ("buffered_pcm", C.c_int64)]
 
 
+class SchedEventC(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("slot", C.c_int32), ("step_idx", C.c_int32), ("n_tokens", C.c_int32), ("n_prs", C.c_int32),
+                ("channel_id", C.c_uint64), ("time", C.c_double), ("marker_id", C.c_int64), ("buffered_pcm", C.c_int64),
+                ("tokens", C.c_uint32 * 64), ("prs", C.c_float * 8)]
+
+
+class SchedStatsC(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("ticks", "steps", "idle_sleeps", "frames", "gather_ns", "step_wait_ns", "fanout_ns")]
+
+
 class LmOptionsC(C.Structure):
     _fields_ = [("kv_dtype", C.c_int32), ("reserved", C.c_int32 * 7)]
 
@@ -167,6 +177,18 @@ SIGNATURES = {
     "dsm_spm_piece": (C.c_char_p, [_P, C.c_int32]),
     "dsm_spm_decode": (C.c_int32, [_P, _P, C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dsm_sched_create": (C.c_int32, [_P, C.c_int32, C.POINTER(_P)]),
+    "dsm_sched_create_multi": (C.c_int32, [C.POINTER(_P), C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "dsm_sched_num_devices": (C.c_int32, [_P]),
+    "dsm_sched_slots_per_device": (C.c_int32, [_P]),
+    "dsm_sched_push_audio_ch": (C.c_int32, [_P, C.c_int32, C.c_uint64, _P, C.c_int64]),
+    "dsm_sched_push_marker_ch": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_int64]),
+    "dsm_sched_close_ch": (C.c_int32, [_P, C.c_int32, C.c_uint64]),
+    "dsm_sched_start": (C.c_int32, [_P]),
+    "dsm_sched_stop": (C.c_int32, [_P]),
+    "dsm_sched_poll": (C.c_int32, [_P, C.c_int32, C.POINTER(SchedEventC), C.POINTER(C.c_int32)]),
+    "dsm_sched_get_stats": (C.c_int32, [_P, C.c_int32, C.POINTER(SchedStatsC)]),
+    "dsm_sched_set_dry_step_us": (None, [_P, C.c_int32]),
+    "dsm_sched_device_step_idx": (C.c_int64, [_P, C.c_int32]),
     "dsm_sched_destroy": (None, [_P]),
     "dsm_sched_open": (C.c_int32, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "dsm_sched_close": (C.c_int32, [_P, C.c_int32]),

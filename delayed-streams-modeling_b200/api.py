@@ -302,12 +302,23 @@ class BatchedAsr:
 
     KINDS = {0: "step", 1: "word", 2: "end_word", 3: "marker", 4: "ready"}
 
-    def __init__(self, asr: Optional[AsrState], batch_size: int = 0):
+    def __init__(self, asr, batch_size: int = 0, n_devices: int = 1):
+        """``asr``: one ``AsrState``, a list of them (one per GPU: device g owns slots [g*B, (g+1)*B)), or None for a
+        dry scheduler over ``n_devices`` x ``batch_size`` slots."""
         self._lib = _lib.load()
-        self.asr = asr
         self._h = C.c_void_p()
-        check(self._lib.dsm_sched_create(asr._h if asr is not None else None, batch_size, C.byref(self._h)))
-        self.batch_size = asr.batch_size() if asr is not None else batch_size
+        asrs = list(asr) if isinstance(asr, (list, tuple)) else ([asr] if asr is not None else [])
+        self.asr = asrs[0] if asrs else None
+        self._asrs = asrs
+        if len(asrs) > 1 or (not asrs and n_devices > 1):
+            n = len(asrs) or n_devices
+            arr = (C.c_void_p * n)(*[a._h for a in asrs]) if asrs else None
+            check(self._lib.dsm_sched_create_multi(arr, n, batch_size, C.byref(self._h)))
+        else:
+            check(self._lib.dsm_sched_create(asrs[0]._h if asrs else None, batch_size, C.byref(self._h)))
+        self.n_devices = self._lib.dsm_sched_num_devices(self._h)
+        self.slots_per_device = self._lib.dsm_sched_slots_per_device(self._h)
+        self.batch_size = self.slots_per_device            # rows of last_mask() / batch_pcm() (device 0)
 
     def close_handle(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -321,15 +332,49 @@ class BatchedAsr:
         check(self._lib.dsm_sched_open(self._h, C.byref(slot), C.byref(cid)))
         return slot.value, cid.value
 
-    def close(self, slot: int):
-        check(self._lib.dsm_sched_close(self._h, slot))
+    def close(self, slot: int, channel_id: int = 0):
+        check(self._lib.dsm_sched_close_ch(self._h, slot, channel_id))
 
-    def push_audio(self, slot: int, pcm):
+    def push_audio(self, slot: int, pcm, channel_id: int = 0):
         a = np.ascontiguousarray(np.asarray(pcm, dtype=np.float32).reshape(-1))
-        check(self._lib.dsm_sched_push_audio(self._h, slot, ptr(a), a.size))
+        check(self._lib.dsm_sched_push_audio_ch(self._h, slot, channel_id, ptr(a), a.size))
 
-    def push_marker(self, slot: int, marker_id: int):
-        check(self._lib.dsm_sched_push_marker(self._h, slot, marker_id))
+    def push_marker(self, slot: int, marker_id: int, channel_id: int = 0):
+        check(self._lib.dsm_sched_push_marker_ch(self._h, slot, channel_id, marker_id))
+
+    def start(self):
+        """One pipelined tick thread per device; drain messages with ``poll``."""
+        check(self._lib.dsm_sched_start(self._h))
+
+    def stop(self):
+        check(self._lib.dsm_sched_stop(self._h))
+
+    def poll(self, slot: int) -> Optional[dict]:
+        ev, got = _lib.SchedEventC(), C.c_int32(0)
+        check(self._lib.dsm_sched_poll(self._h, slot, C.byref(ev), C.byref(got)))
+        if not got.value:
+            return None
+        d = {"kind": self.KINDS[ev.kind], "slot": ev.slot, "channel_id": ev.channel_id, "step_idx": ev.step_idx}
+        if ev.kind == 1:
+            d.update(tokens=[int(ev.tokens[j]) for j in range(ev.n_tokens)], start_time=ev.time)
+        elif ev.kind == 2:
+            d.update(stop_time=ev.time)
+        elif ev.kind == 0:
+            d.update(prs=[float(ev.prs[j]) for j in range(ev.n_prs)], buffered_pcm=ev.buffered_pcm)
+        elif ev.kind == 3:
+            d.update(marker_id=ev.marker_id)
+        return d
+
+    def stats(self, device: int = 0) -> dict:
+        st = _lib.SchedStatsC()
+        check(self._lib.dsm_sched_get_stats(self._h, device, C.byref(st)))
+        return {n: getattr(st, n) for n, _ in st._fields_}
+
+    def set_dry_step_us(self, us: int):
+        self._lib.dsm_sched_set_dry_step_us(self._h, us)
+
+    def device_step_idx(self, device: int) -> int:
+        return self._lib.dsm_sched_device_step_idx(self._h, device)
 
     def tick(self) -> Tuple[bool, List[dict]]:
         stepped = C.c_int32(0)

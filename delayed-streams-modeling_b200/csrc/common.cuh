@@ -57,14 +57,15 @@ inline void check_launch(const char* what) {
 }
 
 // ---- programmatic dependent launch ---------------------------------------------------------------
-// Every step kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization and begins with
+// With DSM_PDL=1 every step kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization; each begins with
 //     pdl_launch_dependents();   // the next kernel of the stream / graph branch may be scheduled once all of this
 //                                // grid's CTAs have started
 //     pdl_wait();                // ... but nothing of THIS grid touches global memory before its predecessors have
 //                                // completed and flushed
 // so a kernel's launch latency, CTA rasterisation and (for the tensor-core GEMMs) barrier / TMEM / descriptor setup
 // overlap the tail of the kernel before it, inside the captured frame graph too.  A kernel launched through
-// launch_k() MUST call pdl_wait() before its first global access.  DSM_PDL=0 launches plainly (A/B).
+// launch_k() MUST call pdl_wait() before its first global access.  Off by default: measured slower on the two-branch
+// frame graph (see pdl_enabled() in runtime.cu); without the launch attribute both instructions are no-ops.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -461,6 +461,15 @@ void AsrImpl::enqueue(bool with_mimi, bool timing) {
 }
 
 void AsrImpl::step(const float* pcm, const uint32_t* codes, const uint8_t* mask, uint32_t* text_tokens) {
+  step_begin(pcm, codes, mask);
+  step_end(text_tokens);
+}
+
+// Enqueues one step without waiting for it: H2D of the inputs, the frame graph, D2H of the sampled tokens.  `pcm` /
+// `codes` must stay untouched until step_end() (the batched scheduler double-buffers its pinned batch so that the
+// gather of frame t+1 overlaps the device work of frame t).
+void AsrImpl::step_begin(const float* pcm, const uint32_t* codes, const uint8_t* mask) {
+  DSM_CHECK(!in_flight, DSM_ERR_INVALID_ARG, "step_begin: the previous step has not been finished with step_end");
   const bool with_mimi = pcm != nullptr;
   DSM_CHECK(with_mimi || codes, DSM_ERR_INVALID_ARG, "either pcm or codes is required");
   DSM_CHECK(!with_mimi || (mimi && mimi->spec.with_encoder), DSM_ERR_INVALID_ARG, "step_pcm needs a Mimi handle with an encoder");
@@ -475,8 +484,9 @@ void AsrImpl::step(const float* pcm, const uint32_t* codes, const uint8_t* mask,
     DSM_CUDA(cudaMemcpyAsync(codes_in, codes, (size_t)B * n_cb * 4, cudaMemcpyDefault, sl));
   }
   DSM_CUDA(cudaEventRecord(ev_t0, sl));
-  const bool use_graph = graphs_enabled();
-  if (use_graph) {
+  flight_graph = graphs_enabled();
+  flight_mimi = with_mimi;
+  if (flight_graph) {
     GraphExec& g = with_mimi ? graph_pcm : graph_tokens;
     if (!g.ready()) g.capture(sl, [&] { enqueue(with_mimi, false); });
     g.launch(sl);
@@ -487,11 +497,18 @@ void AsrImpl::step(const float* pcm, const uint32_t* codes, const uint8_t* mask,
   // the one device->host read of the step (asr.rs:202,217)
   DSM_CUDA(cudaMemcpyAsync(h_sampled, sampled, (size_t)B * 4, cudaMemcpyDeviceToHost, sl));
   if (nh > 0) DSM_CUDA(cudaMemcpyAsync(h_prs, prs, (size_t)nh * B * 4, cudaMemcpyDeviceToHost, sl));
-  DSM_CUDA(cudaStreamSynchronize(sl));
+  in_flight = true;
+}
+
+void AsrImpl::step_end(uint32_t* text_tokens) {
+  DSM_CHECK(in_flight, DSM_ERR_INVALID_ARG, "step_end without step_begin");
+  in_flight = false;
+  DSM_CUDA(cudaSetDevice(lm->device));
+  DSM_CUDA(cudaStreamSynchronize(lm->stream));
   DSM_CUDA(cudaEventElapsedTime(&last_ms[0], ev_t0, ev_t1));
-  if (!use_graph) {
+  if (!flight_graph) {
     DSM_CUDA(cudaEventElapsedTime(&last_ms[2], ev_l0, ev_l1));
-    if (with_mimi) DSM_CUDA(cudaEventElapsedTime(&last_ms[1], ev_m0, ev_m1));
+    if (flight_mimi) DSM_CUDA(cudaEventElapsedTime(&last_ms[1], ev_m0, ev_m1));
     else last_ms[1] = -1.f;
   } else {
     last_ms[1] = last_ms[2] = -1.f;

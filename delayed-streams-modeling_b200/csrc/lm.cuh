@@ -123,6 +123,9 @@ struct AsrImpl {
   AsrImpl(MimiImpl* mimi, LmImpl* lm, int delay, float temperature);
   ~AsrImpl();
   void step(const float* pcm, const uint32_t* codes, const uint8_t* mask, uint32_t* text_tokens);
+  void step_begin(const float* pcm, const uint32_t* codes, const uint8_t* mask);   // asynchronous half
+  void step_end(uint32_t* text_tokens);                                            // waits, runs the word machine
+  bool in_flight = false, flight_graph = false, flight_mimi = false;
   void reset();
   void reset_batch_idx(int b);
 

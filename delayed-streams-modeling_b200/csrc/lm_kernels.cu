@@ -57,6 +57,8 @@ void launch_embed_sum(const uint32_t* text_ids, const uint32_t* audio_ids, int n
 // RMSNorm (batched_transformer.rs:181-198, eps 1e-8): x * rsqrt(mean(x^2) + eps) * alpha, f32 math,
 // bf16 (GEMM operand) and optional f32 outputs.  One CTA per stream.
 // ================================================================================================
+constexpr int kMaxPartials = 16;   // == TC_MAX_SPLIT (gemm_tc.cu)
+
 // Split-K partial sums of the projection that precedes the norm ([S][B][D] planes, see gemm_tc.cuh) are folded into
 // the residual stream here, in split order: x <- x + (P_0 + P_1 + ... + P_{S-1}).
 __global__ void __launch_bounds__(256) rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ partials, int S,
@@ -72,11 +74,15 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(float* __restrict__ x, con
   for (int c = tid * 4; c < D; c += blockDim.x * 4) {
     float4 v = *reinterpret_cast<const float4*>(row + c);
     if (S > 0) {
+      // all planes requested before the first add (the loop bound is a run-time value: unrolled by hand to 16)
+      float4 q[kMaxPartials];
+#pragma unroll
+      for (int sp = 0; sp < kMaxPartials; ++sp)
+        if (sp < S) q[sp] = __ldcg(reinterpret_cast<const float4*>(partials + sp * part_stride + (long long)b * D + c));
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int sp = 0; sp < S; ++sp) {
-        const float4 q = __ldcg(reinterpret_cast<const float4*>(partials + sp * part_stride + (long long)b * D + c));
-        acc.x += q.x, acc.y += q.y, acc.z += q.z, acc.w += q.w;
-      }
+#pragma unroll
+      for (int sp = 0; sp < kMaxPartials; ++sp)
+        if (sp < S) acc.x += q[sp].x, acc.y += q[sp].y, acc.z += q[sp].z, acc.w += q[sp].w;
       v.x += acc.x, v.y += acc.y, v.z += acc.z, v.w += acc.w;
       *reinterpret_cast<float4*>(row + c) = v;
     }
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(float* __restrict__ x, con
 
 void launch_rmsnorm(float* x, const PartialSums& ps, const float* alpha, float eps, int B, int D, __nv_bfloat16* out_bf16,
                     float* out_f32, cudaStream_t st) {
-  DSM_CHECK(D % 4 == 0, DSM_ERR_UNSUPPORTED, "rmsnorm: D=%d", D);
+  DSM_CHECK(D % 4 == 0 && ps.count <= kMaxPartials, DSM_ERR_UNSUPPORTED, "rmsnorm: D=%d, %d partial planes", D, ps.count);
   launch_k(rmsnorm_kernel, B, 256, 0, st, x, ps.planes, ps.count, ps.stride, alpha, eps, D, out_bf16, out_f32);
   check_launch("rmsnorm");
 }
@@ -117,11 +123,14 @@ void launch_rmsnorm(float* x, const PartialSums& ps, const float* alpha, float e
 // The QKV projection may arrive as split-K partial planes [S][B][3*H*D] (S > 0): they are added here, in split order.
 __device__ __forceinline__ float2 load_qkv2(const float* __restrict__ qkv, int S, long long stride, long long off) {
   if (S == 0) return *reinterpret_cast<const float2*>(qkv + off);
+  float2 v[kMaxPartials];
+#pragma unroll
+  for (int sp = 0; sp < kMaxPartials; ++sp)
+    if (sp < S) v[sp] = __ldcg(reinterpret_cast<const float2*>(qkv + sp * stride + off));
   float2 a = make_float2(0.f, 0.f);
-  for (int sp = 0; sp < S; ++sp) {
-    const float2 v = __ldcg(reinterpret_cast<const float2*>(qkv + sp * stride + off));
-    a.x += v.x, a.y += v.y;
-  }
+#pragma unroll
+  for (int sp = 0; sp < kMaxPartials; ++sp)
+    if (sp < S) a.x += v[sp].x, a.y += v[sp].y;
   return a;
 }
 
@@ -691,16 +700,34 @@ __global__ void __launch_bounds__(256) argmax_kernel(float* __restrict__ logits,
   float* row = logits + (long long)b * V;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int j = tid; j < V; j += blockDim.x) {
-    float v;
-    if (S > 0) {
-      v = 0.f;
-      for (int sp = 0; sp < S; ++sp) v += __ldcg(partials + sp * part_stride + (long long)b * V + j);
-      row[j] = v;
-    } else {
-      v = row[j];
+  if (S > 0 && V % 4 == 0) {
+    for (int j = tid * 4; j < V; j += blockDim.x * 4) {
+      float4 q[kMaxPartials];
+#pragma unroll
+      for (int sp = 0; sp < kMaxPartials; ++sp)
+        if (sp < S) q[sp] = __ldcg(reinterpret_cast<const float4*>(partials + sp * part_stride + (long long)b * V + j));
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int sp = 0; sp < kMaxPartials; ++sp)
+        if (sp < S) a.x += q[sp].x, a.y += q[sp].y, a.z += q[sp].z, a.w += q[sp].w;
+      *reinterpret_cast<float4*>(row + j) = a;
+      if (a.x > best) best = a.x, bi = j;
+      if (a.y > best) best = a.y, bi = j + 1;
+      if (a.z > best) best = a.z, bi = j + 2;
+      if (a.w > best) best = a.w, bi = j + 3;
     }
-    if (v > best) best = v, bi = j;
+  } else {
+    for (int j = tid; j < V; j += blockDim.x) {
+      float v;
+      if (S > 0) {
+        v = 0.f;
+        for (int sp = 0; sp < S; ++sp) v += __ldcg(partials + sp * part_stride + (long long)b * V + j);
+        row[j] = v;
+      } else {
+        v = row[j];
+      }
+      if (v > best) best = v, bi = j;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

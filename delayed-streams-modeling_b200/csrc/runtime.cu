@@ -222,7 +222,11 @@ void fill_u32(uint32_t* dst, size_t n, uint32_t v, cudaStream_t st) {
 static int g_graphs_override = -1;   // -1: follow DSM_NO_GRAPH, 0/1: forced by dsm_set_graphs
 void set_graphs_enabled(int v) { g_graphs_override = v; }
 bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("DSM_PDL"); return !(e && e[0] == '0'); }();
+  // Measured on B200 at 256 streams (profiles/r02b_*): no gain for either branch of the frame graph alone (LM 5.27 vs
+  // 5.25 ms, codec 2.92 vs 2.84 ms) and a LOSS when they run side by side (7.68 vs 7.18 ms): early-resident CTAs
+  // spinning in griddepcontrol.wait hold the SM's registers / shared memory that the other branch's kernels could use.
+  // So it is opt-in (DSM_PDL=1).
+  static const bool on = [] { const char* e = getenv("DSM_PDL"); return e && e[0] == '1'; }();
   return on;
 }
 

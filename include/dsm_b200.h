@@ -279,6 +279,12 @@ typedef struct dsm_sched_out {
 /* asr may be NULL for a dry scheduler (slot / queue / marker logic only, no device step); then
  * batch_size_if_no_asr gives B. */
 dsm_status dsm_sched_create(dsm_asr* asr, int32_t batch_size_if_no_asr, dsm_sched** out);
+/* One scheduler over n_devices GPUs: asrs[g] is the asr::State living on device g (all with the same batch B);
+ * device g owns slots [g*B, (g+1)*B) -- streams never interact, so routing is device = slot / B and there is no
+ * step-path exchange.  asrs == NULL (or all NULL): dry scheduler over n_devices x batch_size_if_no_asr slots. */
+dsm_status dsm_sched_create_multi(dsm_asr* const* asrs, int32_t n_devices, int32_t batch_size_if_no_asr, dsm_sched** out);
+int32_t dsm_sched_num_devices(const dsm_sched* h);
+int32_t dsm_sched_slots_per_device(const dsm_sched* h);
 void dsm_sched_destroy(dsm_sched* h);
 /* BatchedAsr::channels (batched_asr.rs:795-808): takes a free slot or fails with DSM_ERR_CAPACITY.  The
  * slot's model state is reset before its first step (InMsg::Init, :567-573). */
@@ -291,6 +297,36 @@ dsm_status dsm_sched_push_marker(dsm_sched* h, int32_t slot, int64_t id);       
 dsm_status dsm_sched_tick(dsm_sched* h, int32_t* stepped);
 int32_t dsm_sched_out_count(const dsm_sched* h);
 dsm_status dsm_sched_out_get(const dsm_sched* h, int32_t i, dsm_sched_out* out);
+/* Variants that name the connection: a stale client whose slot was closed, reclaimed and re-opened by someone else is
+ * refused (DSM_ERR_INVALID_ARG) instead of reaching the new connection (the reference's per-connection channels,
+ * batched_asr.rs:110-118).  channel_id 0 = unchecked.  A slot has ONE producer thread (its connection): the PCM and
+ * marker queues are lock-free single-producer / single-consumer rings (2^17 samples = 5.5 s; DSM_ERR_CAPACITY when a
+ * push does not fit). */
+dsm_status dsm_sched_push_audio_ch(dsm_sched* h, int32_t slot, uint64_t channel_id, const float* pcm, int64_t n);
+dsm_status dsm_sched_push_marker_ch(dsm_sched* h, int32_t slot, uint64_t channel_id, int64_t id);
+dsm_status dsm_sched_close_ch(dsm_sched* h, int32_t slot, uint64_t channel_id);
+/* Threaded mode: one thread per device runs the pipelined loop (gather of frame t+1 into the other half of a
+ * double-buffered pinned batch while the GPU runs frame t; sleeps 2 ms when no slot has a frame, batched_asr.rs:398-400)
+ * and queues each connection's messages; the connection's thread drains them with dsm_sched_poll.  dsm_sched_tick is
+ * refused while the threads run. */
+typedef struct dsm_sched_event {
+  int32_t kind, slot, step_idx, n_tokens, n_prs;
+  uint64_t channel_id;
+  double time;
+  int64_t marker_id, buffered_pcm;
+  uint32_t tokens[64];
+  float prs[8];
+} dsm_sched_event;
+dsm_status dsm_sched_start(dsm_sched* h);
+dsm_status dsm_sched_stop(dsm_sched* h);
+dsm_status dsm_sched_poll(dsm_sched* h, int32_t slot, dsm_sched_event* ev, int32_t* got);
+typedef struct dsm_sched_stats {
+  int64_t ticks, steps, idle_sleeps, frames;
+  int64_t gather_ns, step_wait_ns, fanout_ns;   /* summed over the ticks of the device */
+} dsm_sched_stats;
+dsm_status dsm_sched_get_stats(const dsm_sched* h, int32_t device, dsm_sched_stats* out);
+void dsm_sched_set_dry_step_us(dsm_sched* h, int32_t us);   /* dry mode: pretend a device step takes this long */
+int64_t dsm_sched_device_step_idx(const dsm_sched* h, int32_t device);
 int32_t dsm_sched_free_slots(const dsm_sched* h);
 int64_t dsm_sched_step_idx(const dsm_sched* h);
 /* The mask [B] and the gathered batch [B,1920] of the last tick (host memory; for tests). */

@@ -61,3 +61,56 @@ def test_scheduler_matches_manual_stepping():
         steps = [o for o in outs if o["kind"] == "step"]
         assert sorted(o["slot"] for o in steps) == [i for i in range(B) if mask[i]]
         assert all(len(o["prs"]) == lspec.extra_heads_num for o in steps)
+
+
+def test_threaded_router_matches_manual_stepping():
+    """Pipelined tick thread (step_begin / step_end, double-buffered pinned batch) + event queues: whatever way the
+    frames end up batched, every connection receives exactly the words of an AsrState fed its frames."""
+    import time
+    from dsm_b200 import api
+    B, frames = 3, 14
+    mspec, lspec = tiny_mimi(), tiny_lm(text_in_vocab_size=9, text_out_vocab_size=8)
+    mw, lw = mimi_weights(mspec, seed=0, layer_scale=0.5, decoder=False), lm_weights(lspec, seed=0)
+
+    def build():
+        m = api.Mimi(mspec, mw, B, decoder=False)
+        l = api.LmModel(lspec, lw, B)
+        return api.AsrState(m, l), m, l
+
+    asr_s, *keep_s = build()
+    sched = api.BatchedAsr(asr_s)
+    asr_m, *keep_m = build()
+    audio = synth_audio(B, frames)
+    conns = [sched.open() for _ in range(2)]
+    sched.start()
+    try:
+        for f in range(frames):
+            for slot, cid in conns:
+                sched.push_audio(slot, frame(audio, f)[slot], channel_id=cid)
+            if f % 3 == 0:
+                time.sleep(0.01)                               # let the ticks interleave with the pushes
+        deadline = time.time() + 30
+        while time.time() < deadline and sched.stats(0)["frames"] < frames * len(conns):
+            time.sleep(0.005)
+        time.sleep(0.05)
+    finally:
+        sched.stop()
+    assert sched.stats(0)["frames"] == frames * len(conns)
+    got = {slot: [] for slot, _ in conns}
+    for slot, _ in conns:
+        while True:
+            e = sched.poll(slot)
+            if e is None:
+                break
+            if e["kind"] == "word":
+                got[slot].append((tuple(e["tokens"]), e["start_time"]))
+    want = {slot: [] for slot, _ in conns}
+    mask = np.zeros(B, np.uint8)
+    for slot, _ in conns:
+        mask[slot] = 1
+        asr_m.reset_batch_idx(slot)
+    for f in range(frames):
+        for m in asr_m.step_pcm(frame(audio, f), mask):
+            if m[0] == "word":
+                want[m[3]].append((tuple(m[1]), m[2]))
+    assert got == want

@@ -87,3 +87,113 @@ def test_errors():
         s.push_audio(0, np.zeros(4, np.float32))                    # slot not open
     with pytest.raises(DsmError):
         s.push_audio(5, np.zeros(4, np.float32))                    # out of range
+
+
+def test_stale_connection_is_refused():
+    """A client of a closed connection must not reach whoever re-opened its slot (batched_asr.rs:110-118)."""
+    s = api.BatchedAsr(None, 1)
+    a, cid = s.open()
+    s.push_audio(a, np.zeros(FRAME, np.float32), channel_id=cid)
+    s.close(a, channel_id=cid)
+    s.tick()
+    a2, cid2 = s.open()
+    assert a2 == a and cid2 != cid
+    for call in (lambda: s.push_audio(a, np.zeros(4, np.float32), channel_id=cid),
+                 lambda: s.push_marker(a, 1, channel_id=cid), lambda: s.close(a, channel_id=cid)):
+        with pytest.raises(DsmError):
+            call()
+    s.push_audio(a2, np.zeros(4, np.float32), channel_id=cid2)
+
+
+def test_marker_position_is_taken_when_it_arrives():
+    """batched_asr.rs:577-585 evaluates `current_data` when the Marker message is processed in the connection's message
+    order: audio pushed AFTER the marker must not delay it."""
+    s = api.BatchedAsr(None, 1)
+    a, _ = s.open()
+    s.push_audio(a, np.zeros(FRAME * 2, np.float32))
+    s.push_marker(a, 9)                                             # 2 frames ahead of it
+    s.push_audio(a, np.zeros(FRAME * 5, np.float32))                # later audio
+    fired = []
+    for _ in range(4):
+        fired.append([o["marker_id"] for o in s.tick()[1] if o["kind"] == "marker"])
+    assert fired == [[], [9], [], []]
+
+
+def test_queue_capacity_is_reported():
+    s = api.BatchedAsr(None, 1)
+    a, _ = s.open()
+    s.push_audio(a, np.zeros(1 << 17, np.float32))                  # exactly the ring
+    with pytest.raises(DsmError) as e:
+        s.push_audio(a, np.zeros(1, np.float32))
+    assert e.value.code == -7
+    s.tick()
+    s.push_audio(a, np.zeros(FRAME, np.float32))                    # a frame was consumed: room again
+
+
+def test_multi_device_routing_and_independent_ticks():
+    """Device g owns slots [g*B, (g+1)*B); connections are spread over the devices; each device steps on its own."""
+    nd, B = 4, 3
+    s = api.BatchedAsr(None, B, n_devices=nd)
+    assert s.n_devices == nd and s.slots_per_device == B and s.free_slots() == nd * B
+    opened = [s.open() for _ in range(nd * B)]
+    slots = sorted(x[0] for x in opened)
+    assert slots == list(range(nd * B))
+    # least-loaded placement: the first nd connections land on nd different devices
+    assert sorted(x[0] // B for x in opened[:nd]) == list(range(nd))
+    with pytest.raises(DsmError):
+        s.open()
+    # only device 2's slots get audio: only device 2 steps
+    for sl in range(2 * B, 3 * B):
+        s.push_audio(sl, np.full(FRAME, float(sl), np.float32))
+    stepped, outs = s.tick()
+    assert stepped and [s.device_step_idx(g) for g in range(nd)] == [0, 0, 1, 0]
+    assert sorted(o["slot"] for o in outs if o["kind"] == "ready") == list(range(nd * B))
+    st = s.stats(2)
+    assert st["steps"] == 1 and st["frames"] == B and s.stats(0)["frames"] == 0
+
+
+def test_threaded_mode_delivers_every_frame_and_marker():
+    """One tick thread per device, a pusher thread per group of connections, events drained with poll: nothing is
+    lost, per-connection order is kept, the marker arrives after the frames queued ahead of it."""
+    import threading
+    import time
+    nd, B, frames = 2, 8, 40
+    s = api.BatchedAsr(None, B, n_devices=nd)
+    conns = [s.open() for _ in range(nd * B)]
+    s.start()
+    try:
+        def pusher(group):
+            for f in range(frames):
+                for slot, cid in group:
+                    while True:
+                        try:
+                            s.push_audio(slot, np.zeros(FRAME, np.float32), channel_id=cid)
+                            break
+                        except DsmError:
+                            time.sleep(0.001)               # ring full: the client waits
+                if f == 9:
+                    for slot, cid in group:
+                        s.push_marker(slot, 1000 + slot, channel_id=cid)
+        threads = [threading.Thread(target=pusher, args=(conns[i::4],)) for i in range(4)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        deadline = time.time() + 20
+        while time.time() < deadline and min(s.stats(g)["frames"] for g in range(nd)) < frames * B:
+            time.sleep(0.01)
+        time.sleep(0.05)
+    finally:
+        s.stop()
+    assert [s.stats(g)["frames"] for g in range(nd)] == [frames * B] * nd
+    for slot, cid in conns:
+        evs = []
+        while True:
+            e = s.poll(slot)
+            if e is None:
+                break
+            evs.append(e)
+        assert evs[0]["kind"] == "ready" and all(e["channel_id"] == cid for e in evs)
+        marks = [e for e in evs if e["kind"] == "marker"]
+        assert [m["marker_id"] for m in marks] == [1000 + slot]
+        assert marks[0]["step_idx"] >= 10                    # 10 frames were queued ahead of it
