@@ -87,6 +87,11 @@ void launch_codec_attention(const float* qkv, const RingState& rs, const uint8_t
 void launch_rvq_select(const float* scores, int B, int bins, const float* embedding /*[bins,qdim]*/, int qdim,
                        float* residual, long long res_stride, uint32_t* codes, int n_q, int q, cudaStream_t st,
                        __nv_bfloat16* planes = nullptr, long long plane_stride = 0);
+// The whole split-RVQ encode as one cluster kernel (rvq_fused.cu): embT [n_q][qdim][bins], c2 [n_q][bins],
+// emb [n_q][bins][qdim], resid [B][2*qdim] (first | rest group projections) -> codes [B][n_q].
+bool rvq_fused_supported(int bins, int qdim);
+void launch_rvq_fused(const float* embT, const float* c2, const float* emb, const float* resid, int B, int n_q, int bins,
+                      int qdim, uint32_t* codes, cudaStream_t st);
 // decode: out[b, :] = sum_q E_q[codes[b,q], :] over q in [q0, q1)  (quantization.rs:231-248)
 void launch_rvq_gather_sum(const uint32_t* codes, int n_q, int q0, int q1, const float* embeddings /*[n_q][bins][qdim]*/,
                            int bins, int qdim, int B, float* out, cudaStream_t st);

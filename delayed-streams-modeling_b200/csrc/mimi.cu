@@ -525,20 +525,33 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
     std::vector<float> wr = nq > 1 ? get("quantizer.rvq_rest.input_proj.weight", (size_t)qd * D, 1.f / sqrtf((float)D), 0.f)
                                    : std::vector<float>((size_t)qd * D, 0.f);
     wf.insert(wf.end(), wr.begin(), wr.end());
+    // One-kernel RVQ (rvq_fused.cu) at serving batch sizes; the GEMM + select chain beyond (its tensor-core tiles are
+    // then full) and for codebook shapes the fused kernel does not take.  DSM_RVQ_FUSED_MAX=0 forces the chain (A/B).
+    static const int fused_max = [] { const char* e = getenv("DSM_RVQ_FUSED_MAX"); return e ? atoi(e) : 512; }();
+    const bool fused = rvq_fused_supported(bins, qd) && Bc <= fused_max;
     GemmParams gp;
     gp.A = latent, gp.a_map = dense_rows(1, D), gp.M = Bc, gp.N = 2 * qd, gp.K = D;
     gp.out_raw = resid, gp.o_map = dense_rows(1, 2 * qd);
     // the residual also as bf16 planes (same [B, 2*qd] row layout): the 32 score GEMMs read it pre-split
     const long long RP = (long long)Bc * 2 * qd;
-    __nv_bfloat16* resid_pl = codec_presplit_enabled() ? arena.alloc<__nv_bfloat16>((size_t)3 * RP) : nullptr;
+    __nv_bfloat16* resid_pl = (codec_presplit_enabled() && !fused) ? arena.alloc<__nv_bfloat16>((size_t)3 * RP) : nullptr;
     if (resid_pl) gp.out_planes = resid_pl, gp.p_map = dense_rows(1, 2 * qd), gp.out_plane_stride = RP;
     auto g_proj = make_codec_gemm(arena, gp, wf, wsp);
     if (!g_proj->use_tc) resid_pl = nullptr;     // the CUDA-core GEMM does not write planes
     // codebook embeddings on the host once more for the score GEMMs' weight planes
     std::vector<float> emb_host((size_t)nq * bins * qd);
     DSM_CUDA(cudaMemcpy(emb_host.data(), emb_all, emb_host.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    std::vector<std::shared_ptr<CodecGemm>> g_score(nq);
-    for (int q = 0; q < nq; ++q) {
+    float* embT = nullptr;
+    if (fused) {
+      // codebooks transposed to [n_q][qdim][bins]: a chunk of dims x the CTA's bins is then a run of rows
+      std::vector<float> t(emb_host.size());
+      for (int q = 0; q < nq; ++q)
+        for (int j = 0; j < bins; ++j)
+          for (int d = 0; d < qd; ++d) t[((size_t)q * qd + d) * bins + j] = emb_host[((size_t)q * bins + j) * qd + d];
+      embT = arena.upload(t);
+    }
+    std::vector<std::shared_ptr<CodecGemm>> g_score(fused ? 0 : nq);
+    for (int q = 0; q < (fused ? 0 : nq); ++q) {
       GemmParams s;
       s.A = resid + (q == 0 ? 0 : qd), s.a_map = RowMap{1, (long long)2 * qd, (long long)2 * qd};
       s.M = Bc, s.N = bins, s.K = qd;
@@ -552,6 +565,13 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
     float* sc = scores;
     float* emb = emb_all;
     uint32_t* codes = d_codes;
+    const float* c2p = c2_all;
+    if (fused) {
+      enc_plan.push_back([=](cudaStream_t st) {
+        run_codec_gemm(*g_proj, st);
+        launch_rvq_fused(embT, c2p, emb, res, Bc, nq, bins, qd, codes, st);
+      });
+    } else
     enc_plan.push_back([=](cudaStream_t st) {
       run_codec_gemm(*g_proj, st);
       for (int q = 0; q < nq; ++q) {
