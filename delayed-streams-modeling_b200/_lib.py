@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DSM_B200_LIB") or os.path.join(_HERE, "libdsm_b200.so")   # override: A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dsm_b200.h")
 
-DSM_F32, DSM_BF16, DSM_F16, DSM_U32 = 0, 1, 2, 3
+DSM_F32, DSM_BF16, DSM_F16, DSM_U32, DSM_I64 = 0, 1, 2, 3, 4
 FRAME_SIZE = 1920
 MSG_STEP, MSG_WORD, MSG_END_WORD = 0, 1, 2
 
@@ -189,6 +189,14 @@ SIGNATURES = {
     "dsm_sched_get_stats": (C.c_int32, [_P, C.c_int32, C.POINTER(SchedStatsC)]),
     "dsm_sched_set_dry_step_us": (None, [_P, C.c_int32]),
     "dsm_sched_device_step_idx": (C.c_int64, [_P, C.c_int32]),
+    "dsm_sched_push_msg": (C.c_int32, [_P, C.c_int32, C.c_uint64, _P, C.c_size_t]),
+    "dsm_sched_poll_msg": (C.c_int32, [_P, C.c_int32, _P, _P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]),
+    "dsm_session_create": (C.c_int32, [_P, _P, C.POINTER(_P)]),
+    "dsm_session_destroy": (None, [_P]),
+    "dsm_session_push_msg": (C.c_int32, [_P, _P, C.c_size_t]),
+    "dsm_session_poll_msg": (C.c_int32, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]),
+    "dsm_session_steps": (C.c_int64, [_P]),
+    "dsm_session_save_log": (C.c_int32, [_P, C.c_char_p]),
     "dsm_sched_destroy": (None, [_P]),
     "dsm_sched_open": (C.c_int32, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "dsm_sched_close": (C.c_int32, [_P, C.c_int32]),

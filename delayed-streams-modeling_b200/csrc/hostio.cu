@@ -203,6 +203,7 @@ static int dtype_from_name(const std::string& s, size_t* esz) {
   if (s == "BF16") return *esz = 2, DSM_BF16;
   if (s == "F16") return *esz = 2, DSM_F16;
   if (s == "U32") return *esz = 4, DSM_U32;
+  if (s == "I64") return *esz = 8, DSM_I64;
   return -1;
 }
 static const char* dtype_name(int dt, size_t* esz) {
@@ -211,6 +212,7 @@ static const char* dtype_name(int dt, size_t* esz) {
     case DSM_BF16: *esz = 2; return "BF16";
     case DSM_F16: *esz = 2; return "F16";
     case DSM_U32: *esz = 4; return "U32";
+    case DSM_I64: *esz = 8; return "I64";
   }
   fail(DSM_ERR_INVALID_ARG, "unknown dtype %d", dt);
 }

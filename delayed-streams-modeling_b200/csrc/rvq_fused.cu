@@ -186,10 +186,20 @@ rvq_fused_kernel(const float* __restrict__ embT, const float* __restrict__ c2, c
     __syncthreads();
     // ---- residual update r <- r - E[idx] (quantization.rs:226); level 0 leaves the rest-group residual untouched ----
     if (q > 0 && q + 1 < n_q) {
+      // a thread takes one dim of all 16 winning rows: 16 independent loads in flight (one L2 round trip per level on
+      // the critical path instead of 16), then one 64-byte row of the transposed residual
       const float* eq = emb + (long long)q * bins * qdim;
-      for (int i = tid; i < RV_SPC * qdim; i += RV_THREADS) {
-        const int s = i / qdim, d = i % qdim;
-        r_rest[d * RV_SPC + s] -= __ldg(eq + (long long)winner[s] * qdim + d);
+      for (int d = tid; d < qdim; d += RV_THREADS) {
+        float ev[RV_SPC];
+#pragma unroll
+        for (int s = 0; s < RV_SPC; ++s) ev[s] = __ldg(eq + (long long)winner[s] * qdim + d);
+        float4* row = reinterpret_cast<float4*>(r_rest + d * RV_SPC);
+#pragma unroll
+        for (int s4 = 0; s4 < RV_SPC / 4; ++s4) {
+          float4 v = row[s4];
+          v.x -= ev[4 * s4], v.y -= ev[4 * s4 + 1], v.z -= ev[4 * s4 + 2], v.w -= ev[4 * s4 + 3];
+          row[s4] = v;
+        }
       }
     }
     __syncthreads();

@@ -552,6 +552,72 @@ dsm_status dsm_sched_poll(dsm_sched* h, int32_t slot, dsm_sched_event* ev, int32
     memcpy(ev, &e, sizeof e);
   });
 }
+// One connection's wire traffic (batched_asr.rs:894-949 recv loop, :950-985 send loop): MessagePack InMsg bytes in,
+// MessagePack OutMsg bytes out.  Init re-arms the slot reset + Ready (the server itself sends one at open, :894);
+// OggOpus is refused: the Ogg/Opus decoder (kaudio) is outside this library -- decode to PCM and send Audio.
+dsm_status dsm_sched_push_msg(dsm_sched* h, int32_t slot, uint64_t channel_id, const uint8_t* bytes, size_t len) {
+  return guarded_s([&] {
+    DSM_CHECK(h && bytes, DSM_ERR_INVALID_ARG, "handle and bytes are required");
+    SchedSlot& sl = h->impl->checked_open(slot, channel_id);
+    thread_local std::vector<float> pcm;
+    pcm.resize(len / 5 + 16);                       // an f32 sample takes 5 bytes on the wire
+    thread_local std::vector<uint8_t> data;
+    data.resize(len + 16);
+    dsm_wire_in m;
+    const dsm_status st = dsm_wire_decode_in(bytes, len, &m, pcm.data(), (int64_t)pcm.size(), data.data(), (int64_t)data.size());
+    if (st != DSM_OK) throw Error(st, last_error());
+    switch (m.kind) {
+      case DSM_WIRE_IN_INIT: sl.init_pending.store(1, std::memory_order_release); break;
+      case DSM_WIRE_IN_PING: break;
+      case DSM_WIRE_IN_MARKER:
+        DSM_CHECK(sl.markers.push(MarkerIn{m.id, sl.pcm.total_pushed()}), DSM_ERR_CAPACITY, "slot %d: too many pending markers", slot);
+        break;
+      case DSM_WIRE_IN_AUDIO:
+        DSM_CHECK(sl.pcm.push(m.pcm, (size_t)m.n), DSM_ERR_CAPACITY, "slot %d: %lld samples do not fit its queue", slot, (long long)m.n);
+        break;
+      default: fail(DSM_ERR_UNSUPPORTED, "OggOpus payloads must be decoded to PCM before they reach the scheduler");
+    }
+  });
+}
+// Pops the connection's next event as OutMsg bytes; Word text comes from the SentencePiece model (batched_asr.rs:667)
+// or, without one, is the decimal token ids joined by spaces.  *got = 0 when nothing is queued.
+dsm_status dsm_sched_poll_msg(dsm_sched* h, int32_t slot, dsm_spm* spm, uint8_t* buf, size_t cap, size_t* len, int32_t* got) {
+  return guarded_s([&] {
+    DSM_CHECK(h && buf && len && got, DSM_ERR_INVALID_ARG, "handle, buffer, len and got are required");
+    SchedSlot& sl = h->impl->checked(slot);
+    Event e;
+    *got = sl.events.pop(e) ? 1 : 0;
+    *len = 0;
+    if (!*got) return;
+    dsm_wire_out m{};
+    std::string text;
+    switch (e.kind) {
+      case DSM_SCHED_READY: m.kind = DSM_WIRE_OUT_READY; break;
+      case DSM_SCHED_MARKER: m.kind = DSM_WIRE_OUT_MARKER, m.id = e.marker_id; break;
+      case DSM_SCHED_END_WORD: m.kind = DSM_WIRE_OUT_END_WORD, m.time = e.time; break;
+      case DSM_SCHED_STEP:
+        m.kind = DSM_WIRE_OUT_STEP, m.step_idx = e.step_idx, m.prs = e.prs, m.n_prs = e.n_prs, m.buffered_pcm = e.buffered_pcm;
+        break;
+      case DSM_SCHED_WORD: {
+        m.kind = DSM_WIRE_OUT_WORD, m.time = e.time;
+        if (spm) {
+          char tmp[1024];
+          size_t n = 0;
+          const dsm_status st = dsm_spm_decode(spm, e.tokens, e.n_tokens, tmp, sizeof tmp, &n);
+          if (st != DSM_OK) throw Error(st, last_error());
+          text.assign(tmp, n);
+        } else {
+          for (int i = 0; i < e.n_tokens; ++i) text += (i ? " " : "") + std::to_string(e.tokens[i]);
+        }
+        m.text = text.data(), m.text_len = (int32_t)text.size();
+        break;
+      }
+      default: fail(DSM_ERR_INVALID_ARG, "unknown event kind %d", e.kind);
+    }
+    const dsm_status st = dsm_wire_encode_out(&m, buf, cap, len);
+    if (st != DSM_OK) throw Error(st, last_error());
+  });
+}
 dsm_status dsm_sched_get_stats(const dsm_sched* h, int32_t device, dsm_sched_stats* st) {
   return guarded_s([&] {
     DSM_CHECK(h && st && device >= 0 && device < h->impl->n_dev, DSM_ERR_INVALID_ARG, "handle, stats and a valid device are required");

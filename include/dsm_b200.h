@@ -41,7 +41,7 @@ enum {
   DSM_ERR_CAPACITY = -7 /* no free slot (the reference closes the socket with code 4000, protocol.rs:33) */
 };
 
-enum { DSM_F32 = 0, DSM_BF16 = 1, DSM_F16 = 2, DSM_U32 = 3 };
+enum { DSM_F32 = 0, DSM_BF16 = 1, DSM_F16 = 2, DSM_U32 = 3, DSM_I64 = 4 /* token logs only */ };
 
 #define DSM_FRAME_SIZE 1920 /* moshi-server/src/batched_asr.rs:26 */
 
@@ -406,6 +406,26 @@ int32_t dsm_spm_vocab_size(const dsm_spm* h);
 const char* dsm_spm_piece(const dsm_spm* h, int32_t id);
 /* Token ids of one word -> UTF-8 text (NUL-terminated in buf); *len = length in bytes. */
 dsm_status dsm_spm_decode(dsm_spm* h, const uint32_t* ids, int32_t n, char* buf, size_t cap, size_t* len);
+
+/* ---- a connection's wire traffic through the scheduler (batched_asr.rs:894-985) ------------------------------- */
+/* InMsg bytes in: Init re-arms reset + Ready, Audio / Marker / Ping as the push_* calls; OggOpus is DSM_ERR_UNSUPPORTED
+ * (decode to PCM first: the Ogg/Opus decoder is outside this library). */
+dsm_status dsm_sched_push_msg(dsm_sched* h, int32_t slot, uint64_t channel_id, const uint8_t* bytes, size_t len);
+/* The connection's next queued event (threaded mode) as OutMsg bytes; Word text through `spm` (NULL: token ids). */
+dsm_status dsm_sched_poll_msg(dsm_sched* h, int32_t slot, dsm_spm* spm, uint8_t* buf, size_t cap, size_t* len, int32_t* got);
+
+/* ---- single-connection session: the non-batched Asr module (moshi-server/src/asr.rs:95-330) ------------------ */
+/* One asr::State of batch size 1 driven by a connection's wire messages: Audio of any length is cut into frames and
+ * stepped (Mimi encode + LM), AsrMsgs leave as OutMsg bytes with SentencePiece text (`spm` may be NULL: token ids),
+ * and every step's tokens are kept for the log the reference writes at the end of a connection (asr.rs:126-176). */
+typedef struct dsm_session dsm_session;
+dsm_status dsm_session_create(dsm_asr* asr_batch1, dsm_spm* spm, dsm_session** out);
+void dsm_session_destroy(dsm_session* s);
+dsm_status dsm_session_push_msg(dsm_session* s, const uint8_t* bytes, size_t len);
+dsm_status dsm_session_poll_msg(dsm_session* s, uint8_t* buf, size_t cap, size_t* len, int32_t* got);
+int64_t dsm_session_steps(const dsm_session* s);
+/* safetensors with "text" [1, steps] and "audio" [1, codebooks, steps], I64 */
+dsm_status dsm_session_save_log(const dsm_session* s, const char* safetensors_path);
 
 #ifdef __cplusplus
 }

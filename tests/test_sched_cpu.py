@@ -197,3 +197,54 @@ def test_threaded_mode_delivers_every_frame_and_marker():
         marks = [e for e in evs if e["kind"] == "marker"]
         assert [m["marker_id"] for m in marks] == [1000 + slot]
         assert marks[0]["step_idx"] >= 10                    # 10 frames were queued ahead of it
+
+
+def test_wire_messages_through_the_scheduler():
+    """A connection's MessagePack traffic (batched_asr.rs:894-985): InMsg bytes in, OutMsg bytes out."""
+    import ctypes as C
+    import time
+
+    import msgpack
+    from dsm_b200 import _lib
+    from dsm_b200._lib import check
+    lib = _lib.load()
+    s = api.BatchedAsr(None, 2)
+    slot, cid = s.open()
+
+    def push(obj):
+        b = msgpack.packb(obj, use_single_float=True)
+        buf = (C.c_uint8 * len(b)).from_buffer_copy(b)
+        return lib.dsm_sched_push_msg(s._h, slot, cid, buf, len(b))
+
+    def poll_all():
+        out = []
+        buf = (C.c_uint8 * 4096)()
+        n, got = C.c_size_t(0), C.c_int32(0)
+        while True:
+            check(lib.dsm_sched_poll_msg(s._h, slot, None, buf, 4096, C.byref(n), C.byref(got)))
+            if not got.value:
+                return out
+            out.append(msgpack.unpackb(bytes(buf[:n.value])))
+
+    s.start()
+    try:
+        assert push({"type": "Audio", "pcm": [0.0] * (FRAME * 3)}) == 0
+        assert push({"type": "Marker", "id": 5}) == 0
+        assert push({"type": "Ping"}) == 0
+        assert push({"type": "OggOpus", "data": [1, 2, 3]}) == -5          # no Opus decoder in this library
+        assert push({"type": "Nope"}) == -1
+        deadline = time.time() + 10
+        msgs = []
+        while time.time() < deadline and not any(m["type"] == "Marker" for m in msgs):
+            msgs += poll_all()
+            time.sleep(0.005)
+        assert push({"type": "Init"}) == 0                                   # a client Init: reset + Ready again
+        deadline = time.time() + 10
+        while time.time() < deadline and sum(m["type"] == "Ready" for m in msgs) < 2:
+            msgs += poll_all()
+            time.sleep(0.005)
+    finally:
+        s.stop()
+    assert msgs[0] == {"type": "Ready"}
+    assert {"type": "Marker", "id": 5} in msgs
+    assert sum(m["type"] == "Ready" for m in msgs) == 2
