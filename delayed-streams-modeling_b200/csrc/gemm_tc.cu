@@ -382,11 +382,13 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
   static const int env_split = [] { const char* e = getenv("DSM_TC_MAXSPLIT"); return e ? std::min(atoi(e), TC_MAX_SPLIT) : TC_MAX_SPLIT; }();
   g.split_k = 1;
   if (mode != TC_GATE_BF16) {
-    // fill the 148 SMs by splitting K (at least 4 k-blocks per split)
+    // fill the 148 SMs by splitting K (at least 4 k-blocks per split) -- only when the tiles alone leave SMs idle:
+    // every split writes and the consumer re-reads an [M, N] f32 plane, which at 2,000 streams is 50-250 MB per GEMM
+    // (measured: 41.7 vs 37.1 ms per step with and without splits there)
     const int kb = K / TC_BK;
     const long long base = (long long)n_tiles * ceil_div(M, g.bmx);
     double best = 0.0;
-    for (int s = 1; s <= env_split; ++s) {
+    for (int s = 1; s <= (base >= 148 ? 1 : env_split); ++s) {
       const int per = ceil_div(kb, s);
       if (per < 4 && s > 1) break;
       const int s_eff = ceil_div(kb, per);
