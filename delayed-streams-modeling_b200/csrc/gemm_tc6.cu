@@ -300,8 +300,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      // with two TMEM buffers the two epilogue warp groups (one warp per lane quadrant each) take alternate tiles
-      mbar_init(&acc_empty[s], (p.acc_bufs == 2 && p.split_k == 1) ? T6_EPI_WARPS / 2 : T6_EPI_WARPS);
+      mbar_init(&acc_empty[s], T6_EPI_WARPS);
     }
     for (int s = 0; s < WS; ++s) {
       mbar_init(&w_full[s], 1);
@@ -506,13 +505,10 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int quad = warp & 3, sib = ew >> 2;     // sibling index 0/1 within the quadrant
     float* scratch = scratch_all + ew * SR * T6_SCR_LD;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    // Short-K layers are bound by this epilogue (a chain of dependent latencies per tile: accumulator ready ->
-    // TMEM load -> transposition -> residual / stores): with two TMEM buffers each sibling group owns one buffer and
-    // a whole tile, so two tiles' epilogues are in flight per SM instead of one.
-    const bool alt = AB == 2 && S == 1;
+    // (Tried: the two sibling groups taking alternate tiles, one TMEM buffer each, so that two tiles' epilogues are in
+    // flight per SM -- measured slower, codec step 3.10 vs 2.87 ms: a tile then drains through 4 warps instead of 8.)
     int li = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
-      if (alt && (li & 1) != sib) continue;
       const int tile = item / S, split = item % S;
       const int pm = min(p.pm, min(kb_per, num_kb - split * kb_per));
       const int tile_n = p.nj * BN;
@@ -536,8 +532,8 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       tc_fence_after();
       const uint32_t acc_addr = lane_addr + buf * buf_stride;
       const int n_chunks = nj * BN / 32;
-      const bool split_rows = !alt && n_chunks == 1;   // both siblings work on chunk 0, half the rows each
-      const int c_first = (alt || split_rows) ? 0 : sib, c_step = (alt || split_rows) ? 1 : 2;
+      const bool split_rows = n_chunks == 1;       // both siblings work on chunk 0, half the rows each
+      const int c_first = split_rows ? 0 : sib, c_step = split_rows ? 1 : 2;
       const int qrow = lane >> 3, cs = lane & 7;   // 8 lanes per row: 8 x float4 = one 128-byte segment
 #pragma unroll 1
       for (int c = c_first; c < n_chunks; c += c_step) {
