@@ -468,6 +468,25 @@ def run_ours(args):
                     "launches_per_step": lspec.num_layers,
                     "share_of_step": avg_ms * lspec.num_layers / step_ms,
                     "how": "CUDA events around every attention launch over %d eager LM steps with full rings" % n_prof}
+    if asr is not None:
+        # the LM decode step on its own (north_star: "the decode step >= 70 % of HBM roofline"): the same frame graph
+        # without the codec branch, fed codes; full rings; device-timed over the same number of steps
+        codes_dev_lm = torch.from_numpy(np.random.default_rng(7).integers(0, 2048, (B, lspec.audio_codebooks)).astype(np.int32)).cuda()
+        for _ in range(3):
+            asr.step_tokens(codes_dev_lm, None, want_messages=False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(rig.ext)
+        for _ in range(args.steps):
+            asr.step_tokens(codes_dev_lm, None, want_messages=False)
+        e1.record(rig.ext)
+        barrier()
+        lm_ms = max_over_ranks(e0.elapsed_time(e1), world, "cuda") / args.steps
+        if roofline is not None:
+            lm_bytes = sum(v for k, v in step_parts.items() if k.startswith("lm_"))
+            roofline["lm_step_ms"] = lm_ms
+            roofline["lm_step_bytes"] = lm_bytes
+            roofline["lm_step_frac"] = lm_bytes / (lm_ms * 1e-3) / 1e9 / peak
     if roofline is not None:
         # the whole step against the HBM roofline (SURVEY 8(d) bytes; `frac` above is the dominant kernel alone)
         roofline["step_frac"] = step_frac
