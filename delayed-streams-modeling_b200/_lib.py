@@ -264,7 +264,12 @@ class WeightTable:
         arr = (Tensor * n)()
         for i, (name, a) in enumerate(weights.items()):
             if hasattr(a, "numpy"):
-                a = a.detach().cpu().numpy()
+                a = a.detach().cpu()
+                if str(a.dtype) == "torch.bfloat16":      # numpy has no bf16: hand the bit patterns over as DSM_BF16
+                    import torch
+                    a = a.contiguous().view(torch.int16).numpy().view(np.uint16)
+                else:
+                    a = a.numpy()
             if a.dtype == np.float32:
                 dt = DSM_F32
             elif a.dtype == np.float16:

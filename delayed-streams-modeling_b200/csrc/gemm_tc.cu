@@ -337,20 +337,20 @@ bool tc_gemm_supported(int M, int N, int K, int mode) {
   return true;
 }
 
-// OCC2: half the pipeline stages (~100 KB of shared memory) so that two CTAs share an SM and one's prologue / epilogue
-// overlaps the other's K loop (DSM_TC_OCC2=1; the split-K selection then aims at 2 x 148 CTAs).
-template <int BMX, int MODE, int NACC, bool OCC2 = false>
+// (Tried: half the stages, ~100 KB, so that two CTAs share an SM and one's prologue / epilogue overlaps the other's K
+// loop, with twice the splits: LM branch 5.41 vs 5.26 ms -- slower, removed.)
+template <int BMX, int MODE, int NACC>
 struct TcCfg {
   static constexpr int STAGE_BYTES = NACC * TC_BN * TC_BK * 2 + BMX * TC_BK * 2;
-  static constexpr int RAW = ((OCC2 ? 104 : 200) * 1024) / STAGE_BYTES;
+  static constexpr int RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = RAW > 8 ? 8 : RAW;
   static_assert(STAGES >= 2, "need at least two pipeline stages");
   static constexpr int SMEM = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;   // barriers, tmem slot, last flag
 };
 
-template <int BMX, int MODE, int NACC, bool OCC2 = false>
+template <int BMX, int MODE, int NACC>
 static void launch_tc(const TcGemm& g, cudaStream_t st) {
-  using C = TcCfg<BMX, MODE, NACC, OCC2>;
+  using C = TcCfg<BMX, MODE, NACC>;
   auto kern = tc_gemm_kernel<BMX, MODE, NACC, C::STAGES>;
   static PerDeviceOnce attr;
   attr.run([&] { DSM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); });
@@ -391,9 +391,7 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
     const int kb = K / TC_BK;
     const long long base = (long long)n_tiles * ceil_div(M, g.bmx);
     double best = 0.0;
-    static const bool occ2 = [] { const char* e = getenv("DSM_TC_OCC2"); return e && e[0] == '1'; }();
-    g.occ2 = occ2 && mode != TC_GATE_BF16;
-    const long long wave = g.occ2 ? 296 : 148;
+    const long long wave = 148;
     for (int s = 1; s <= (base >= wave ? 1 : env_split); ++s) {
       const int per = ceil_div(kb, s);
       if (per < 4 && s > 1) break;
@@ -429,7 +427,7 @@ void tc_reduce_partials(const TcGemm& g, cudaStream_t st) {
 
 void tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
 #define TC_CASE(BMX, MODE, NACC) \
-  if (g.bmx == BMX && g.mode == MODE && g.nacc == NACC) return g.occ2 ? launch_tc<BMX, MODE, NACC, true>(g, st) : launch_tc<BMX, MODE, NACC>(g, st);
+  if (g.bmx == BMX && g.mode == MODE && g.nacc == NACC) return launch_tc<BMX, MODE, NACC>(g, st);
   TC_CASE(64, TC_STORE_F32, 1) TC_CASE(128, TC_STORE_F32, 1) TC_CASE(256, TC_STORE_F32, 1)
   TC_CASE(64, TC_ACCUM_F32, 1) TC_CASE(128, TC_ACCUM_F32, 1) TC_CASE(256, TC_ACCUM_F32, 1)
   TC_CASE(64, TC_GATE_BF16, 2) TC_CASE(128, TC_GATE_BF16, 2)

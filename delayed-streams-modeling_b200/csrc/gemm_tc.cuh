@@ -30,7 +30,6 @@ struct TcGemm {
   int bmx = 0;         // streams per tile: 64, 128 or 256
   int nacc = 1;        // weight sub-tiles (TMEM accumulators) per CTA
   int split_k = 1;
-  bool occ2 = false;   // two CTAs per SM (half the pipeline stages), see gemm_tc.cu
   int mode = TC_STORE_F32;
   int hidden = 0;      // TC_GATE_BF16: N = 2 * hidden
   float* out_f32 = nullptr;            // STORE: [M, N];  ACCUM: x [M, N] (+=)   (split_k == 1, or after tc_reduce_partials)

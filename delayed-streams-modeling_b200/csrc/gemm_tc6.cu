@@ -193,20 +193,13 @@ constexpr int T6_PLANE = T6_BM * T6_BK * 2;      // 16 KB per bf16 plane tile
 constexpr int T6_EPI_WARPS = 8;      // two per TMEM lane quadrant
 constexpr int T6_CVT_WARPS = 4;      // one converter thread per tile row
 constexpr int T6_THREADS = (4 + T6_CVT_WARPS + T6_EPI_WARPS) * 32;
-#ifndef T6_TS
-#define T6_TS 1
-#endif
-// T6_TS: the f32-A variant keeps the converted A planes in TENSOR MEMORY (tcgen05.st by the converter warps, MMAs
-// with A from TMEM) instead of shared memory; the 96 KB go to a third staging slot and two more W stages.
-constexpr int T6_NSTG = T6_TS ? 3 : 2;           // f32 staging slots
+// The f32-A variant keeps the converted A planes in TENSOR MEMORY (tcgen05.st by the converter warps, MMAs with A from
+// TMEM); shared memory then holds three f32 staging slots and the W ring.  (The round-1 variant with the planes in
+// shared memory measured slower -- codec step 2.98 vs 2.90 ms -- and is gone.)
+constexpr int T6_NSTG = 3;                       // f32 staging slots
 constexpr int T6_ACC_COLS_TS = 320;              // TMEM columns [0, 320): accumulators; [320, 512): two A buffers
 constexpr int T6_A_COLS = 96;                    // TMEM columns of one A buffer: 3 planes x 32 (64 bf16 per row)
 constexpr int T6_NPL_PRE = 3;        // operand-plane buffers of the pre-split variant (48 KB each)
-#ifndef T6_NPL_F32
-#define T6_NPL_F32 2
-#endif
-// Operand-plane buffers of the f32-A variant.  Measured: two buffers + two W stages beat one buffer + four W
-// stages (codec step 3.01 vs 3.17 ms), so the converter/MMA overlap is worth more than the deeper W ring.
 constexpr int T6_SCR_LD = 36;        // floats per scratch row: 32 columns + 4 (float4 rows stay conflict-free)
 
 }  // namespace
@@ -252,8 +245,8 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzle atoms need a 1024-byte aligned base
-  constexpr bool TS = !PRE && T6_TS;             // A planes in tensor memory
-  constexpr int NPL = PRE ? T6_NPL_PRE : (TS ? 2 : T6_NPL_F32);      // operand-plane buffers (TS: in TMEM)
+  constexpr bool TS = !PRE;                      // f32 A: planes in tensor memory
+  constexpr int NPL = PRE ? T6_NPL_PRE : 2;      // operand-plane buffers (TS: in TMEM)
   constexpr int NSTG = T6_NSTG;
   uint8_t* stg = smem;                           // [NSTG][T6_STG]   (absent with PRE)
   uint8_t* planes = stg + (PRE ? 0 : NSTG * T6_STG);   // [NPL][3][T6_PLANE]   (absent with TS)
@@ -440,9 +433,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (lane == 0) mbar_arrive(&stg_empty[s]);      // staging slot may be refilled
         const int ps = kit % NPL;
         mbar_wait(&pl_empty[ps], ((kit / NPL) & 1) ^ 1);  // MMAs that read this plane buffer are done
-        if (TS) tc_fence_after();
-        else fence_proxy_async();                         // async-proxy reads before the generic stores below
-        uint8_t* dst = planes + ps * 3 * T6_PLANE + r * 128;
+        tc_fence_after();
         // TS: thread r owns TMEM lane r (the converter warps 4..7 reach lane quadrants 0..3); 32 columns per plane
         const uint32_t tdst = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + T6_ACC_COLS_TS + ps * T6_A_COLS;
         uint32_t h1[4], h2[4], h3[4];
@@ -465,7 +456,7 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const float s0 = r0 - __uint_as_float(v0 & 0xffff0000u), s1 = r1 - __uint_as_float(v1 & 0xffff0000u);
             p3[e] = __byte_perm(__float_as_uint(s0), __float_as_uint(s1), 0x7632);
           }
-          if (TS) {
+          {
             // eight floats -> four packed columns per plane; stored eight columns at a time
             if (cc & 1) {
               uint32_t q1[8] = {h1[0], h1[1], h1[2], h1[3], p1[0], p1[1], p1[2], p1[3]};
@@ -478,19 +469,10 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 4; ++e) h1[e] = p1[e], h2[e] = p2[e], h3[e] = p3[e];
             }
-          } else {
-            const int chunk = (cc ^ sw) << 4;
-            *reinterpret_cast<uint4*>(dst + chunk) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-            *reinterpret_cast<uint4*>(dst + T6_PLANE + chunk) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
-            *reinterpret_cast<uint4*>(dst + 2 * T6_PLANE + chunk) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
           }
         }
-        if (TS) {
-          tmem_st_wait();
-          tc_fence_before();
-        } else {
-          fence_proxy_async();      // make the generic-proxy stores visible to the tensor core (async proxy)
-        }
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&pl_full[ps]);
       }
@@ -549,7 +531,8 @@ tc6_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int rr = half * SR + 4 * q + qrow;
             const uint32_t ro = __shfl_sync(0xffffffffu, res_off, rr);
             const bool want = p.res && col_ok && ((ok_mask >> rr) & 1u) && !(split_rows && half / (PARTS / 2) != sib) && S == 1;
-            rres[half][q] = want ? __ldg(reinterpret_cast<const float4*>(p.res + ro + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // `res` may alias `out_raw` (x <- x + ...): a coherent load, not ld.global.nc
+            rres[half][q] = want ? __ldcg(reinterpret_cast<const float4*>(p.res + ro + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         float v[32];
@@ -711,8 +694,7 @@ template <int BN, bool PRE>
 struct T6Cfg {
   static constexpr int W_STAGE = 3 * BN * T6_BK * 2;
   // f32 staging (2 x 32 KB) + two operand-plane buffers, or three plane buffers fed directly by TMA
-  static constexpr int FIXED = PRE ? T6_NPL_PRE * 3 * T6_PLANE
-                                   : T6_NSTG * T6_STG + (T6_TS ? 0 : T6_NPL_F32 * 3 * T6_PLANE);
+  static constexpr int FIXED = PRE ? T6_NPL_PRE * 3 * T6_PLANE : T6_NSTG * T6_STG;
   static constexpr int SCRATCH = T6_EPI_WARPS * (PRE ? 8 : 16) * T6_SCR_LD * 4;
   static constexpr int WS_RAW = (232448 - 512 - FIXED - SCRATCH) / W_STAGE;
   static constexpr int WS = WS_RAW > 6 ? 6 : WS_RAW;
@@ -738,8 +720,7 @@ static void launch6(const Tc6Gemm& g, cudaStream_t st) {
   p.out_raw = g.ep.out_raw, p.o_map = g.ep.o_map, p.out_act = g.ep.out_act, p.e_map = g.ep.e_map;
   p.out_pl = g.ep.out_planes, p.pl_map = g.ep.p_map, p.pl_stride = g.ep.out_plane_stride;
   const long long tiles = (long long)p.m_tiles * p.n_groups * g.split_k;
-  static const int max_ctas = [] { const char* e = getenv("DSM_TC6_MAXCTAS"); int v = e ? atoi(e) : 0; return v > 0 ? v : 148; }();
-  const int grid = (int)std::min<long long>(tiles, max_ctas);
+  const int grid = (int)std::min<long long>(tiles, 148);
   launch_k(kern, grid, T6_THREADS, C::SMEM, st, g.map_a, g.map_w, p);
   check_launch("tc6_gemm");
 }
@@ -812,7 +793,7 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes,
   // column sub-tiles per CTA: as many as TMEM holds (512 columns) while the grid still covers the SMs
   // (TMEM: two tile buffers of 256 columns, each shared by the correction accumulator and >= 1 main
   // accumulator => at most 128 output columns per tile)
-  static const int max_tile_n = [] { const char* e = getenv("DSM_TC6_TILE_N"); int v = e ? atoi(e) : 0; return v >= 32 ? v : (T6_TS ? 64 : 128); }();
+  constexpr int max_tile_n = 64;
   // pre-split A: one column sub-tile per CTA keeps the W ring as deep (in k-blocks) as the operand ring
   int nj = std::max(1, std::min(n_sub, std::min(g.a_planes ? 64 : 128, max_tile_n) / t.bn));
   while (nj > 1 && m_tiles * ceil_div(n_sub, nj) < 148) nj = (nj + 1) / 2;
@@ -822,7 +803,7 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes,
   // (> 8 k-blocks) want more rotating accumulators than that leaves and take the whole region as one buffer
   // (the tensor core truncates when it accumulates: see the MMA issuer).
   {
-    const bool ts = T6_TS && !g.a_planes;
+    const bool ts = !g.a_planes;
     const int acc_cols = ts ? T6_ACC_COLS_TS : 512;
     const int tile_n = nj * t.bn;
     const bool long_k = ts && ceil_div(g.K, T6_BK) > 8;
@@ -839,7 +820,8 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes,
     // save (codec step 3.94 ms with, 3.83 ms without), so deterministic split-K is opt-in
     // (DSM_TC6_SPLITK=1) and only considered where >= 6 k-blocks remain per split.
     static const bool splitk_on = [] { const char* e = getenv("DSM_TC6_SPLITK"); return e && e[0] == '1'; }();
-    if (splitk_on && wsp.ws && tiles <= 74 && num_kb >= 16) {
+    // (the last-arrival reduce path does not write plane outputs: such GEMMs never split)
+    if (splitk_on && wsp.ws && tiles <= 74 && num_kb >= 16 && !g.out_planes) {
       S = (int)std::max<long long>(1, std::min<long long>(148 / tiles, num_kb / 6));
       const int per = ceil_div(num_kb, S);
       S = ceil_div(num_kb, per);

@@ -525,9 +525,10 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
     std::vector<float> wr = nq > 1 ? get("quantizer.rvq_rest.input_proj.weight", (size_t)qd * D, 1.f / sqrtf((float)D), 0.f)
                                    : std::vector<float>((size_t)qd * D, 0.f);
     wf.insert(wf.end(), wr.begin(), wr.end());
-    // One-kernel RVQ (rvq_fused.cu) at serving batch sizes; the GEMM + select chain beyond (its tensor-core tiles are
-    // then full) and for codebook shapes the fused kernel does not take.  DSM_RVQ_FUSED_MAX=0 forces the chain (A/B).
-    static const int fused_max = [] { const char* e = getenv("DSM_RVQ_FUSED_MAX"); return e ? atoi(e) : 512; }();
+    // One-kernel RVQ (rvq_fused.cu): correct (codes identical) but measured SLOWER than the GEMM + select chain -- codec
+    // step 3.36 vs 2.93 ms at 256 streams, equal at 64 (its 128 CTAs pull 32 MB of codebook slices per level through
+    // L2) -- so it is opt-in: DSM_RVQ_FUSED_MAX=<largest batch that uses it> (default 0 = never).
+    static const int fused_max = [] { const char* e = getenv("DSM_RVQ_FUSED_MAX"); return e ? atoi(e) : 0; }();
     const bool fused = rvq_fused_supported(bins, qd) && Bc <= fused_max;
     GemmParams gp;
     gp.A = latent, gp.a_map = dense_rows(1, D), gp.M = Bc, gp.N = 2 * qd, gp.K = D;

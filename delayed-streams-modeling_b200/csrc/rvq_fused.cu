@@ -14,8 +14,10 @@
 //     updates its own copy of the residual from the winning codebook row.
 // CUDA cores, not tensor cores, on purpose: with 16 streams per cluster the MMA N dimension would be 16, where
 // tcgen05 issue rate, not math, bounds the tile -- the f32 FMA pipe does the same work in the same time, exactly.
-// Used for batches up to DSM_RVQ_FUSED_MAX streams (default 512); larger batches keep the GEMM + select chain,
-// whose tensor-core tiles are then full.
+// MEASURED (B200, profiles/r02e): slower than the GEMM + select chain it was meant to replace -- codec step 3.36 vs
+// 2.93 ms at 256 streams, equal at 64.  The 16 clusters each stream the whole codebook level (128 CTAs x 256 KB = 32 MB
+// of L2 reads per level, the same 2 MB sixteen times) and a level costs ~34 us instead of the ~6 us the FMA count
+// allows.  Kept opt-in (DSM_RVQ_FUSED_MAX) with its parity test; the chain stays the default.
 #include "kernels.cuh"
 
 namespace dsm {
