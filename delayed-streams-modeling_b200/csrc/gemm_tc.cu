@@ -380,7 +380,10 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
   // the SM's L2 port, so narrower stream tiles multiply the X traffic; to cover the 148 SMs we split K
   // instead (same total bytes, more CTAs); the partial sums are added in split order by the consuming kernel
   // (deterministic).  The gate pair has a non-linear epilogue, so it does not split.
-  g.bmx = M <= 64 ? 64 : (M <= 128 ? 128 : (mode == TC_GATE_BF16 ? 128 : 256));
+  // The gate pair holds two accumulators: 128 streams per tile while that is what covers the SMs (256 streams: 88
+  // CTAs instead of 44), 256 -- all 512 TMEM columns, twice the MMAs per operand byte -- once the batch fills them
+  const long long gate_tiles_256 = (long long)ceil_div(n_rows, TC_BN) * ceil_div(M, 256);
+  g.bmx = M <= 64 ? 64 : (M <= 128 ? 128 : ((mode == TC_GATE_BF16 && gate_tiles_256 < 148) ? 128 : 256));
   // DSM_TC_MAXSPLIT caps split-K (1 = no split: A/B of the partial-sum path)
   static const int env_split = [] { const char* e = getenv("DSM_TC_MAXSPLIT"); return e ? std::min(atoi(e), TC_MAX_SPLIT) : TC_MAX_SPLIT; }();
   g.split_k = 1;
@@ -430,7 +433,7 @@ void tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
   if (g.bmx == BMX && g.mode == MODE && g.nacc == NACC) return launch_tc<BMX, MODE, NACC>(g, st);
   TC_CASE(64, TC_STORE_F32, 1) TC_CASE(128, TC_STORE_F32, 1) TC_CASE(256, TC_STORE_F32, 1)
   TC_CASE(64, TC_ACCUM_F32, 1) TC_CASE(128, TC_ACCUM_F32, 1) TC_CASE(256, TC_ACCUM_F32, 1)
-  TC_CASE(64, TC_GATE_BF16, 2) TC_CASE(128, TC_GATE_BF16, 2)
+  TC_CASE(64, TC_GATE_BF16, 2) TC_CASE(128, TC_GATE_BF16, 2) TC_CASE(256, TC_GATE_BF16, 2)
 #undef TC_CASE
   fail(DSM_ERR_UNSUPPORTED, "tc_gemm: no kernel for bmx=%d mode=%d nacc=%d", g.bmx, g.mode, g.nacc);
 }
