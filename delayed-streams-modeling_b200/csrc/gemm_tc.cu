@@ -395,7 +395,9 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
     const long long base = (long long)n_tiles * ceil_div(M, g.bmx);
     double best = 0.0;
     const long long wave = 148;
-    for (int s = 1; s <= (base >= wave ? 1 : env_split); ++s) {
+    // tiles alone already cover two thirds of the SMs: no split (at 2,000 streams out-proj / MLP-out have 128 tiles;
+    // 8 splits there meant 131 MB of partial planes per GEMM: 89 us per launch instead of ~45, profiles/r02j)
+    for (int s = 1; s <= (base >= 100 ? 1 : env_split); ++s) {
       const int per = ceil_div(kb, s);
       if (per < 4 && s > 1) break;
       const int s_eff = ceil_div(kb, per);

@@ -816,10 +816,10 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes,
     const long long tiles = m_tiles * ceil_div(n_sub, nj);
     const int num_kb = ceil_div(g.K, T6_BK);
     int S = 1;
-    // Measured at 256 streams: the fix-up pass and the extra per-CTA prologues cost what the shorter K loops
-    // save (codec step 3.94 ms with, 3.83 ms without), so deterministic split-K is opt-in
-    // (DSM_TC6_SPLITK=1) and only considered where >= 6 k-blocks remain per split.
-    static const bool splitk_on = [] { const char* e = getenv("DSM_TC6_SPLITK"); return e && e[0] == '1'; }();
+    // On by default since round 2 (measured again on the final kernel: codec step 2.79 vs 2.92 ms at 256 streams, 1.69
+    // vs 1.85 ms at 64, no change at 2,000; round 1 had measured a small loss on a slower kernel).  DSM_TC6_SPLITK=0
+    // turns it off; only considered where >= 6 k-blocks remain per split.
+    static const bool splitk_on = [] { const char* e = getenv("DSM_TC6_SPLITK"); return !(e && e[0] == '0'); }();
     // (the last-arrival reduce path does not write plane outputs: such GEMMs never split)
     if (splitk_on && wsp.ws && tiles <= 74 && num_kb >= 16 && !g.out_planes) {
       S = (int)std::max<long long>(1, std::min<long long>(148 / tiles, num_kb / 6));

@@ -340,6 +340,23 @@ void launch_lm_attention(const __nv_bfloat16* q, const RingState& rs, const uint
 // The query and the probabilities are split into two int8 terms (x ~ s * (x1 + x2 / 254), 15 bits), so the only
 // rounding that matters is the ring's own 8 bits.
 // ================================================================================================
+// One warp per head, a lane owns 4 consecutive channels (two RoPE pairs): q / k / v arrive as one float4 per lane, K
+// leaves as one 32-bit store, and V -- whose bytes for this slot sit at stride 4 in the key-quad layout -- as a
+// read-modify-write of the lane's four words (one coalesced 512-byte row per head each way; nobody else writes the
+// ring, and a (stream, head) belongs to one warp).
+__device__ __forceinline__ float4 load_qkv4(const float* __restrict__ qkv, int S, long long stride, long long off) {
+  if (S == 0) return *reinterpret_cast<const float4*>(qkv + off);
+  float4 v[kMaxPartials];
+#pragma unroll
+  for (int sp = 0; sp < kMaxPartials; ++sp)
+    if (sp < S) v[sp] = __ldcg(reinterpret_cast<const float4*>(qkv + sp * stride + off));
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int sp = 0; sp < kMaxPartials; ++sp)
+    if (sp < S) a.x += v[sp].x, a.y += v[sp].y, a.z += v[sp].z, a.w += v[sp].w;
+  return a;
+}
+
 __global__ void __launch_bounds__(256) rope_scatter_q8_kernel(const float* __restrict__ qkv, int S, long long part_stride,
                                                                RingState rs, int H, int D,
                                                                int context, int ctxp, const float* __restrict__ inv_freq,
@@ -352,29 +369,26 @@ __global__ void __launch_bounds__(256) rope_scatter_q8_kernel(const float* __res
   const int b = blockIdx.x, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int slot = (int)rs.cur_index[b];
   const float pos = (float)rs.rope_pos[b];
-  const int HD = H * D, half = D / 2;
+  const int HD = H * D;
   const long long row = (long long)b * 3 * HD;
+  const int d0 = 4 * lane;                       // this lane's channels [d0, d0 + 4) = pairs 2*lane, 2*lane + 1
+  const bool on = d0 < D;
+  float sn0 = 0.f, cs0 = 1.f, sn1 = 0.f, cs1 = 1.f;
+  if (on) {
+    sincosf(pos * inv_freq[2 * lane], &sn0, &cs0);
+    sincosf(pos * inv_freq[2 * lane + 1], &sn1, &cs1);
+  }
   for (int h = warp; h < H; h += blockDim.x / 32) {
-    // a lane owns the pairs p = lane, lane + 32 (D = 128) or p = lane (D = 64)
-    float kr[4], vr[4];
-    float kmax = 0.f, vmax = 0.f;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int p = lane + 32 * i;
-      kr[2 * i] = kr[2 * i + 1] = vr[2 * i] = vr[2 * i + 1] = 0.f;
-      if (p >= half) continue;
-      float sn, cs;
-      sincosf(pos * inv_freq[p], &sn, &cs);
-      const float2 q = load_qkv2(qkv, S, part_stride, row + h * D + 2 * p);
-      const float2 k = load_qkv2(qkv, S, part_stride, row + HD + h * D + 2 * p);
-      const float2 v = load_qkv2(qkv, S, part_stride, row + 2 * HD + h * D + 2 * p);
-      *reinterpret_cast<__nv_bfloat162*>(q_out + (long long)b * HD + h * D + 2 * p) =
-          __floats2bfloat162_rn(q.x * cs - q.y * sn, q.x * sn + q.y * cs);
-      kr[2 * i] = k.x * cs - k.y * sn, kr[2 * i + 1] = k.x * sn + k.y * cs;
-      vr[2 * i] = v.x, vr[2 * i + 1] = v.y;
-      kmax = fmaxf(kmax, fmaxf(fabsf(kr[2 * i]), fabsf(kr[2 * i + 1])));
-      vmax = fmaxf(vmax, fmaxf(fabsf(v.x), fabsf(v.y)));
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), k = q, v = q;
+    if (on) {
+      q = load_qkv4(qkv, S, part_stride, row + h * D + d0);
+      k = load_qkv4(qkv, S, part_stride, row + HD + h * D + d0);
+      v = load_qkv4(qkv, S, part_stride, row + 2 * HD + h * D + d0);
     }
+    const float kr[4] = {k.x * cs0 - k.y * sn0, k.x * sn0 + k.y * cs0, k.z * cs1 - k.w * sn1, k.z * sn1 + k.w * cs1};
+    const float vr[4] = {v.x, v.y, v.z, v.w};
+    float kmax = fmaxf(fmaxf(fabsf(kr[0]), fabsf(kr[1])), fmaxf(fabsf(kr[2]), fabsf(kr[3])));
+    float vmax = fmaxf(fmaxf(fabsf(vr[0]), fabsf(vr[1])), fmaxf(fabsf(vr[2]), fabsf(vr[3])));
     kmax = warp_max(kmax), vmax = warp_max(vmax);
     const float kinv = kmax > 0.f ? 127.f / kmax : 0.f, vinv = vmax > 0.f ? 127.f / vmax : 0.f;
     const long long bh = (long long)b * H + h;
@@ -382,21 +396,35 @@ __global__ void __launch_bounds__(256) rope_scatter_q8_kernel(const float* __res
       k_scale[bh * ctxp + slot] = kmax / 127.f;
       if (!v_ring_bf16) v_scale[bh * ctxp + slot] = vmax / 127.f;
     }
-    int8_t* kdst = k_ring + (bh * context + slot) * D;
-    int8_t* vdst = v_ring_bf16 ? nullptr : v_ring + bh * ctxp * D + (long long)(slot >> 2) * D * 4 + (slot & 3);
+    if (!on) continue;
+    {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(q.x * cs0 - q.y * sn0, q.x * sn0 + q.y * cs0);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(q.z * cs1 - q.w * sn1, q.z * sn1 + q.w * cs1);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo), u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(q_out + (long long)b * HD + h * D + d0) = u;
+    }
+    int kq[4], vq[4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int p = lane + 32 * i;
-      if (p >= half) continue;
-      const int k0 = __float2int_rn(kr[2 * i] * kinv), k1 = __float2int_rn(kr[2 * i + 1] * kinv);
-      *reinterpret_cast<uint16_t*>(kdst + 2 * p) = (uint16_t)((k0 & 0xff) | ((k1 & 0xff) << 8));
-      if (v_ring_bf16) {
-        *reinterpret_cast<__nv_bfloat162*>(v_ring_bf16 + (bh * context + slot) * D + 2 * p) =
-            __floats2bfloat162_rn(vr[2 * i], vr[2 * i + 1]);
-      } else {
-        vdst[(2 * p) * 4] = (int8_t)__float2int_rn(vr[2 * i] * vinv);
-        vdst[(2 * p + 1) * 4] = (int8_t)__float2int_rn(vr[2 * i + 1] * vinv);
-      }
+    for (int i = 0; i < 4; ++i) kq[i] = __float2int_rn(kr[i] * kinv), vq[i] = __float2int_rn(vr[i] * vinv);
+    *reinterpret_cast<uint32_t*>(k_ring + (bh * context + slot) * D + d0) =
+        (uint32_t)(kq[0] & 0xff) | ((uint32_t)(kq[1] & 0xff) << 8) | ((uint32_t)(kq[2] & 0xff) << 16) | ((uint32_t)(kq[3] & 0xff) << 24);
+    if (v_ring_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(vr[0], vr[1]), hi = __floats2bfloat162_rn(vr[2], vr[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo), u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(v_ring_bf16 + (bh * context + slot) * D + d0) = u;
+    } else {
+      // word d of key quad slot/4 holds channel d of slots 4*(slot/4) .. +3: replace byte slot%4 of four words
+      uint4* vw = reinterpret_cast<uint4*>(v_ring + bh * ctxp * D + (long long)(slot >> 2) * D * 4 + d0 * 4);
+      uint4 w = *vw;
+      const int sh = 8 * (slot & 3);
+      const uint32_t keep = ~(0xffu << sh);
+      w.x = (w.x & keep) | ((uint32_t)(vq[0] & 0xff) << sh);
+      w.y = (w.y & keep) | ((uint32_t)(vq[1] & 0xff) << sh);
+      w.z = (w.z & keep) | ((uint32_t)(vq[2] & 0xff) << sh);
+      w.w = (w.w & keep) | ((uint32_t)(vq[3] & 0xff) << sh);
+      *vw = w;
     }
   }
 }

@@ -114,3 +114,64 @@ def test_threaded_router_matches_manual_stepping():
             if m[0] == "word":
                 want[m[3]].append((tuple(m[1]), m[2]))
     assert got == want
+
+
+def test_router_over_two_devices():
+    """Handles on device 0 AND device 1 in one process (per-device kernel attributes), one scheduler over both:
+    connections are spread over the GPUs and every connection gets the words of a single-device manual run."""
+    import time
+    from dsm_b200 import _lib, api
+    if _lib.load().dsm_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    B, frames = 3, 12
+    mspec, lspec = tiny_mimi(), tiny_lm(text_in_vocab_size=9, text_out_vocab_size=8)
+    mw, lw = mimi_weights(mspec, seed=0, layer_scale=0.5, decoder=False), lm_weights(lspec, seed=0)
+
+    def build(dev):
+        m = api.Mimi(mspec, mw, B, device=dev, decoder=False)
+        l = api.LmModel(lspec, lw, B, device=dev)
+        return api.AsrState(m, l), m, l
+
+    states = [build(0), build(1)]
+    sched = api.BatchedAsr([s[0] for s in states])
+    assert sched.n_devices == 2
+    conns = [sched.open() for _ in range(4)]
+    assert sorted(slot // B for slot, _ in conns) == [0, 0, 1, 1]          # least-loaded placement
+    audio = synth_audio(4, frames)
+    sched.start()
+    try:
+        for f in range(frames):
+            for i, (slot, cid) in enumerate(conns):
+                sched.push_audio(slot, frame(audio, f)[i], channel_id=cid)
+        deadline = time.time() + 60
+        while time.time() < deadline and sum(sched.stats(g)["frames"] for g in range(2)) < frames * len(conns):
+            time.sleep(0.005)
+        time.sleep(0.05)
+    finally:
+        sched.stop()
+    got = []
+    for slot, _ in conns:
+        words = []
+        while True:
+            e = sched.poll(slot)
+            if e is None:
+                break
+            if e["kind"] == "word":
+                words.append((tuple(e["tokens"]), e["start_time"]))
+        got.append(words)
+    ref, *keep = build(0)
+    want = [[] for _ in conns]
+    padded = np.zeros((frames, B, 1920), np.float32)
+    for rnd in range(0, len(conns), B):                                      # B connections at a time through one state
+        ref.reset()
+        group = list(range(rnd, min(rnd + B, len(conns))))
+        mask = np.zeros(B, np.uint8)
+        mask[:len(group)] = 1
+        for f in range(frames):
+            pcm = np.zeros((B, 1920), np.float32)
+            for j, i in enumerate(group):
+                pcm[j] = frame(audio, f)[i]
+            for m in ref.step_pcm(pcm, mask):
+                if m[0] == "word":
+                    want[group[m[3]]].append((tuple(m[1]), m[2]))
+    assert got == want

@@ -12,7 +12,7 @@ from helpers import ROOT
 pytestmark = pytest.mark.gpu
 
 VARIANTS = [
-    ({"DSM_TC6_SPLITK": "1"}, ["tests/test_gpu_codec_gemm.py", "tests/test_gpu_mimi.py"]),
+    ({"DSM_TC6_SPLITK": "0"}, ["tests/test_gpu_codec_gemm.py", "tests/test_gpu_mimi.py"]),
     ({"DSM_CODEC_PRESPLIT": "0"}, ["tests/test_gpu_mimi.py"]),
     ({"DSM_RVQ_FUSED_MAX": "512"}, ["tests/test_gpu_mimi.py", "tests/test_gpu_real_audio.py"]),
     ({"DSM_PDL": "1"}, ["tests/test_gpu_asr.py", "tests/test_gpu_lm.py"]),
