@@ -59,3 +59,18 @@ def test_reference_arm_other_ranks_exit_quietly(monkeypatch, capsys):
     args = type("A", (), dict(ref_streams=1, steps=1, warmup=1, workload="mimi", gpus=2, streams=256, prefill=0))()
     bench.run_reference(args)
     assert capsys.readouterr().out == ""
+
+
+def test_step_algorithmic_bytes_match_survey_8d():
+    """stt-1b, 256 streams, bf16 ring: LM 26.88 GB + Mimi 2.36 GB per step."""
+    import bench
+    from dsm_b200.spec import stt_1b_en_fr
+    spec = stt_1b_en_fr()
+    B = 256
+    kv = 2 * B * spec.num_layers * spec.num_heads * spec.context * spec.head_dim * 2      # K and V, bf16
+    total, parts = bench.step_algorithmic_bytes("asr", B, spec, kv)
+    lm = sum(v for k, v in parts.items() if k.startswith("lm_"))
+    mimi = sum(v for k, v in parts.items() if k.startswith("mimi_"))
+    assert abs(bench.lm_streamed_weight_bytes(spec) - 1.677e9) < 2e6
+    assert abs(lm - 26.88e9) < 0.05e9 and abs(mimi - 2.36e9) < 0.03e9 and abs(total - lm - mimi) < 1
+    assert bench.percentile(list(range(101)), 0.99) == 99 and bench.percentile([5.0], 0.5) == 5.0
