@@ -276,18 +276,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     // They are added IN SPLIT ORDER by the kernel that consumes the result anyway (RMSNorm for the residual
     // projections, RoPE + ring scatter for QKV, the greedy argmax for the text head; tc_reduce_partials for a
     // stand-alone GEMM), so the sum is the same in every run -- no atomics -- and costs no extra launch.
-    const int n = n0 + warp * 32 + lane;
     float* plane = p.partials + (size_t)blockIdx.z * p.M * p.N;
 #pragma unroll 1
-    for (int c = 0; c < BMX; c += 32) {
-      if (m0 + c >= p.M) break;
-      float v[32];
-      tmem_ld32(lane_addr + c, v);
-      if (n < p.N) {
+    for (int a = 0; a < NACC; ++a) {
+      const int n = n0 + a * TC_BN + warp * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BMX; c += 32) {
+        if (m0 + c >= p.M) break;
+        float v[32];
+        tmem_ld32(lane_addr + a * BMX + c, v);
+        if (n < p.N) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int m = m0 + c + i;
-          if (m < p.M) plane[(long long)m * p.N + n] = v[i];
+          for (int i = 0; i < 32; ++i) {
+            const int m = m0 + c + i;
+            if (m < p.M) plane[(long long)m * p.N + n] = v[i];
+          }
         }
       }
     }
@@ -362,7 +365,7 @@ static void launch_tc(const TcGemm& g, cudaStream_t st) {
   p.out_f32 = g.out_f32, p.out_bf16 = g.out_bf16, p.partials = g.partials;
   const int n_rows = MODE == TC_GATE_BF16 ? g.hidden : g.N;
   dim3 grid(ceil_div(n_rows, TC_BN * (MODE == TC_GATE_BF16 ? 1 : NACC)), ceil_div(g.M, BMX), g.split_k);
-  DSM_CHECK(g.split_k == 1 || (NACC == 1 && g.partials), DSM_ERR_INVALID_ARG, "tc_gemm: split_k %d without a partials buffer", g.split_k);
+  DSM_CHECK(g.split_k == 1 || (MODE != TC_GATE_BF16 && g.partials), DSM_ERR_INVALID_ARG, "tc_gemm: split_k %d without a partials buffer", g.split_k);
   launch_k(kern, grid, 128, C::SMEM, st, g.map_w, g.map_x, p);
   check_launch("tc_gemm");
 }
@@ -374,7 +377,12 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
   g.M = M, g.N = N, g.K = K, g.mode = mode, g.out_f32 = out_f32, g.out_bf16 = out_bf16;
   g.hidden = mode == TC_GATE_BF16 ? N / 2 : 0;
   const int n_rows = mode == TC_GATE_BF16 ? g.hidden : N;
-  g.nacc = mode == TC_GATE_BF16 ? 2 : 1;
+  // Two weight sub-tiles per CTA ("wide": 256 weight rows x 256 streams share one activation slab) once the batch is
+  // large enough that the GEMM is bound by the L2 -> SM operand feed rather than by covering the SMs: at 2,000 streams
+  // a 128 x 256 tile pulls 48 KB per k-block for 32 K MACs x 64, a 256 x 256 tile 64 KB for twice that
+  // (profiles/r02l: out-proj / MLP-out at 140 us per launch, ~5 TB/s of operand traffic).  At 256 streams the wide
+  // tile halves the CTA count and measured slower (round 1), so it starts at 512 streams.
+  g.nacc = mode == TC_GATE_BF16 ? 2 : ((M >= 512 && n_rows >= 2 * TC_BN) ? 2 : 1);
   const int n_tiles = ceil_div(n_rows, TC_BN * (mode == TC_GATE_BF16 ? 1 : g.nacc));
   // Stream tile: as wide as the batch allows.  Every CTA must pull its W slab AND its X slab through
   // the SM's L2 port, so narrower stream tiles multiply the X traffic; to cover the 148 SMs we split K
@@ -395,9 +403,9 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
     const long long base = (long long)n_tiles * ceil_div(M, g.bmx);
     double best = 0.0;
     const long long wave = 148;
-    // tiles alone already cover two thirds of the SMs: no split (at 2,000 streams out-proj / MLP-out have 128 tiles;
-    // 8 splits there meant 131 MB of partial planes per GEMM: 89 us per launch instead of ~45, profiles/r02j)
-    for (int s = 1; s <= (base >= 100 ? 1 : env_split); ++s) {
+    // (measured at 2,000 streams: out-proj / MLP-out with 128 tiles and no split 140 us per launch, with 8 splits and
+    // their 131 MB of partial planes 89 us -- the split stays whenever the tiles alone do not fill the SMs)
+    for (int s = 1; s <= (base >= wave ? 1 : env_split); ++s) {
       const int per = ceil_div(kb, s);
       if (per < 4 && s > 1) break;
       const int s_eff = ceil_div(kb, per);
@@ -433,8 +441,8 @@ void tc_reduce_partials(const TcGemm& g, cudaStream_t st) {
 void tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
 #define TC_CASE(BMX, MODE, NACC) \
   if (g.bmx == BMX && g.mode == MODE && g.nacc == NACC) return launch_tc<BMX, MODE, NACC>(g, st);
-  TC_CASE(64, TC_STORE_F32, 1) TC_CASE(128, TC_STORE_F32, 1) TC_CASE(256, TC_STORE_F32, 1)
-  TC_CASE(64, TC_ACCUM_F32, 1) TC_CASE(128, TC_ACCUM_F32, 1) TC_CASE(256, TC_ACCUM_F32, 1)
+  TC_CASE(64, TC_STORE_F32, 1) TC_CASE(128, TC_STORE_F32, 1) TC_CASE(256, TC_STORE_F32, 1) TC_CASE(256, TC_STORE_F32, 2)
+  TC_CASE(64, TC_ACCUM_F32, 1) TC_CASE(128, TC_ACCUM_F32, 1) TC_CASE(256, TC_ACCUM_F32, 1) TC_CASE(256, TC_ACCUM_F32, 2)
   TC_CASE(64, TC_GATE_BF16, 2) TC_CASE(128, TC_GATE_BF16, 2) TC_CASE(256, TC_GATE_BF16, 2)
 #undef TC_CASE
   fail(DSM_ERR_UNSUPPORTED, "tc_gemm: no kernel for bmx=%d mode=%d nacc=%d", g.bmx, g.mode, g.nacc);
