@@ -377,12 +377,18 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
   g.M = M, g.N = N, g.K = K, g.mode = mode, g.out_f32 = out_f32, g.out_bf16 = out_bf16;
   g.hidden = mode == TC_GATE_BF16 ? N / 2 : 0;
   const int n_rows = mode == TC_GATE_BF16 ? g.hidden : N;
-  // Two weight sub-tiles per CTA ("wide": 256 weight rows x 256 streams share one activation slab) once the batch is
-  // large enough that the GEMM is bound by the L2 -> SM operand feed rather than by covering the SMs: at 2,000 streams
-  // a 128 x 256 tile pulls 48 KB per k-block for 32 K MACs x 64, a 256 x 256 tile 64 KB for twice that
-  // (profiles/r02l: out-proj / MLP-out at 140 us per launch, ~5 TB/s of operand traffic).  At 256 streams the wide
-  // tile halves the CTA count and measured slower (round 1), so it starts at 512 streams.
-  g.nacc = mode == TC_GATE_BF16 ? 2 : ((M >= 512 && n_rows >= 2 * TC_BN) ? 2 : 1);
+  // Two weight sub-tiles per CTA ("wide": 256 weight rows x 256 streams share one activation slab: 64 KB of operands
+  // per k-block for twice the MACs of a 128 x 256 tile's 48 KB) for the large-batch regime, where the GEMMs are bound
+  // by the L2 -> SM operand feed (profiles/r02l: ~5 TB/s).  Measured (LM branch alone, int8 ring, `tools/gpu_run_n.sh`):
+  // at 2,000 streams it pays for out-proj / MLP-out, whose 128 narrow tiles would otherwise take an 8-way split with
+  // 131 MB of partial planes (22.1 vs 23.2 ms); it is neutral for QKV / text head there, and at 1,024 streams it costs
+  // 0.9 ms when it leaves QKV with 96 CTAs.  Hence: wide when the narrow grid is about a wave or more AND either the
+  // wide grid still fills the SMs or the narrow one would not have.
+  const long long narrow_tiles = (long long)ceil_div(n_rows, TC_BN) * ceil_div(M, 256);
+  const long long wide_tiles = (long long)ceil_div(n_rows, 2 * TC_BN) * ceil_div(M, 256);
+  const bool wide = mode != TC_GATE_BF16 && M > 256 && n_rows >= 2 * TC_BN && narrow_tiles >= 100 &&
+                    (wide_tiles >= 148 || narrow_tiles < 148);
+  g.nacc = (mode == TC_GATE_BF16 || wide) ? 2 : 1;
   const int n_tiles = ceil_div(n_rows, TC_BN * (mode == TC_GATE_BF16 ? 1 : g.nacc));
   // Stream tile: as wide as the batch allows.  Every CTA must pull its W slab AND its X slab through
   // the SM's L2 port, so narrower stream tiles multiply the X traffic; to cover the 148 SMs we split K
