@@ -52,7 +52,8 @@ def test_stt_2_6b_shaped_layers():
 @pytest.mark.parametrize("M,N,K,mode", [(256, 6144, 2048, 0), (256, 2048, 2048, 1), (256, 11264, 2048, 2),
                                         (256, 2048, 5632, 1), (256, 8000, 2048, 0), (3, 768, 256, 0),
                                         (130, 512, 192, 2), (700, 384, 128, 1), (2000, 256, 128, 0),
-                                        (2000, 11264, 256, 2), (1000, 6144, 512, 0), (1000, 2048, 512, 1)])
+                                        (2000, 11264, 256, 2), (1000, 6144, 512, 0), (1000, 2048, 512, 1),
+                                        (2000, 6144, 256, 0), (2000, 2048, 512, 1), (2000, 8000, 256, 0)])   # wide tiles
 def test_tcgen05_gemm_against_numpy(M, N, K, mode):
     from dsm_b200 import _lib
     from dsm_b200._lib import check, ptr
