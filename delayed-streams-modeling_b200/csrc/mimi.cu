@@ -55,6 +55,10 @@ std::shared_ptr<CodecGemm> make_codec_gemm(Arena& arena, const GemmParams& g_in,
   DSM_CHECK(w_host.size() == (size_t)g.N * g.K, DSM_ERR_SHAPE, "codec gemm: weight has %zu elements, expected %d x %d",
             w_host.size(), g.N, g.K);
   c->use_tc = codec_gemm_tc_enabled() && tc6_supported(g);
+  // Experiment (DSM_CODEC_SIMT_MAXK=k): layers with K <= k are pure epilogue on the tensor-core kernel (one k-block, a
+  // tile's residual loads / stores form one dependent chain per SM); the CUDA-core GEMM keeps many small CTAs in flight.
+  static const int simt_maxk = [] { const char* e = getenv("DSM_CODEC_SIMT_MAXK"); return e ? atoi(e) : 0; }();
+  if (c->use_tc && g.K <= simt_maxk && !g.a_planes && !g.out_planes) c->use_tc = false;
   if (c->use_tc) {
     tc6_prepare(c->t, g, tc6_split_weights(arena, w_host, g.N, g.K), wsp);
   } else {
