@@ -197,6 +197,10 @@ SIGNATURES = {
     "dsm_session_poll_msg": (C.c_int32, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int32)]),
     "dsm_session_steps": (C.c_int64, [_P]),
     "dsm_session_save_log": (C.c_int32, [_P, C.c_char_p]),
+    "dsm_tts_sink_create": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "dsm_tts_sink_destroy": (None, [_P]),
+    "dsm_tts_sink_push": (C.c_int32, [_P, _P, C.c_int64, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "dsm_tts_sink_decode_all": (C.c_int32, [_P, _P, C.c_int64, _P]),
     "dsm_sched_destroy": (None, [_P]),
     "dsm_sched_open": (C.c_int32, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "dsm_sched_close": (C.c_int32, [_P, C.c_int32]),

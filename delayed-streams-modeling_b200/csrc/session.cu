@@ -166,4 +166,67 @@ dsm_status dsm_session_save_log(const dsm_session* s, const char* safetensors_pa
   });
 }
 
+// ---- TTS audio sink: the consumer of Mimi::decode_step in the TTS server -------------------------------------
+// moshi-server/src/tts.rs:512-560 (audio_processing_loop): per generation step the audio tokens [1, codebooks, 1] go
+// through decode_step once step_idx >= text_audio_delay_in_tokens + acoustic_delay, and the PCM frame leaves in the
+// connection's format (Encoder::encode, tts.rs:252-281: raw little-endian f32 or a MessagePack OutMsg::Audio{pcm});
+// :917-929 decodes a finished token matrix chunk by chunk.  The Opus formats need the kaudio encoder (out of scope).
+struct dsm_tts_sink {
+  MimiImpl* mimi;
+  int delay;            // text_audio_delay_in_tokens + acoustic_delay
+  int format;           // 0: Pcm, 1: PcmMessagePack
+  std::vector<float> pcm;
+};
+
+dsm_status dsm_tts_sink_create(dsm_mimi* mimi_decoder, int32_t text_audio_delay_in_tokens, int32_t acoustic_delay, int32_t format,
+                               dsm_tts_sink** out) {
+  return session_guarded([&] {
+    DSM_CHECK(mimi_decoder && out, DSM_ERR_INVALID_ARG, "mimi and out are required");
+    *out = nullptr;
+    DSM_CHECK(mimi_decoder->impl->B == 1 && mimi_decoder->impl->spec.with_decoder, DSM_ERR_INVALID_ARG,
+              "the sink drives a Mimi handle of batch size 1 with a decoder");
+    DSM_CHECK(format == 0 || format == 1, DSM_ERR_UNSUPPORTED, "format %d (0 = Pcm, 1 = PcmMessagePack; Opus needs an encoder outside this library)", format);
+    std::unique_ptr<dsm_tts_sink> s(new dsm_tts_sink);
+    s->mimi = mimi_decoder->impl, s->delay = text_audio_delay_in_tokens + acoustic_delay, s->format = format;
+    s->pcm.resize(DSM_FRAME_SIZE);
+    *out = s.release();
+  });
+}
+void dsm_tts_sink_destroy(dsm_tts_sink* s) { delete s; }
+
+// AudioMessage::Tokens(Some(codes) | None, _, step_idx): *len = bytes written (0: nothing to send for this step).
+dsm_status dsm_tts_sink_push(dsm_tts_sink* s, const uint32_t* codes, int64_t step_idx, uint8_t* buf, size_t cap, size_t* len) {
+  return session_guarded([&] {
+    DSM_CHECK(s && buf && len, DSM_ERR_INVALID_ARG, "sink, buffer and len are required");
+    *len = 0;
+    if (!codes || step_idx < s->delay) return;              // tts.rs:536: only logged
+    s->mimi->decode_step(codes, nullptr, s->pcm.data());
+    if (s->format == 0) {
+      const size_t n = (size_t)DSM_FRAME_SIZE * sizeof(float);
+      *len = n;
+      DSM_CHECK(n <= cap, DSM_ERR_CAPACITY, "frame of %zu bytes, buffer has %zu", n, cap);
+      memcpy(buf, s->pcm.data(), n);                        // little-endian f32, as byteorder::LittleEndian writes them
+    } else {
+      dsm_wire_in m{};
+      m.kind = DSM_WIRE_IN_AUDIO, m.pcm = s->pcm.data(), m.n = DSM_FRAME_SIZE;   // same layout as OutMsg::Audio { pcm }
+      const dsm_status st = dsm_wire_encode_in(&m, buf, cap, len);
+      if (st != DSM_OK) throw Error(st, last_error());
+    }
+  });
+}
+
+// tts.rs:917-929: codes [codebooks, steps] (the reference's [1, cb, T] tensor) -> pcm [steps * 1920], from a fresh state.
+dsm_status dsm_tts_sink_decode_all(dsm_tts_sink* s, const uint32_t* codes, int64_t steps, float* pcm) {
+  return session_guarded([&] {
+    DSM_CHECK(s && codes && pcm && steps >= 0, DSM_ERR_INVALID_ARG, "sink, codes and pcm are required");
+    const int cb = s->mimi->spec.n_q;
+    s->mimi->reset_state();
+    std::vector<uint32_t> frame((size_t)cb);
+    for (int64_t t = 0; t < steps; ++t) {
+      for (int c = 0; c < cb; ++c) frame[c] = codes[(size_t)c * steps + t];
+      s->mimi->decode_step(frame.data(), nullptr, pcm + (size_t)t * DSM_FRAME_SIZE);
+    }
+  });
+}
+
 }  // extern "C"

@@ -427,6 +427,20 @@ int64_t dsm_session_steps(const dsm_session* s);
 /* safetensors with "text" [1, steps] and "audio" [1, codebooks, steps], I64 */
 dsm_status dsm_session_save_log(const dsm_session* s, const char* safetensors_path);
 
+/* ---- TTS audio sink: the consumer of Mimi::decode_step (moshi-server/src/tts.rs:512-560, 917-929) -------------- */
+/* A batch-1 Mimi decoder fed one step's audio tokens at a time: frames are decoded once
+ * step_idx >= text_audio_delay_in_tokens + acoustic_delay and leave in the connection's format -- 0: raw
+ * little-endian f32 (Encoder::Pcm), 1: MessagePack OutMsg::Audio{pcm} (Encoder::PcmMessagePack), tts.rs:252-281.
+ * The text-to-token generation loop (LM with depformer) is not part of this library. */
+typedef struct dsm_tts_sink dsm_tts_sink;
+dsm_status dsm_tts_sink_create(dsm_mimi* mimi_decoder_batch1, int32_t text_audio_delay_in_tokens, int32_t acoustic_delay,
+                               int32_t format, dsm_tts_sink** out);
+void dsm_tts_sink_destroy(dsm_tts_sink* s);
+/* codes [codebooks] of this step or NULL (a step without audio tokens); *len = bytes to send (0: none). */
+dsm_status dsm_tts_sink_push(dsm_tts_sink* s, const uint32_t* codes, int64_t step_idx, uint8_t* buf, size_t cap, size_t* len);
+/* A finished token matrix codes [codebooks, steps] -> pcm [steps * 1920] from a fresh decoder state. */
+dsm_status dsm_tts_sink_decode_all(dsm_tts_sink* s, const uint32_t* codes, int64_t steps, float* pcm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,3 +97,62 @@ def test_session_matches_manual_stepping(tmp_path):
     assert np.array_equal(aud, np.stack(codes, axis=1))
     lib.dsm_session_destroy(sess)
     lib.dsm_spm_close(spm)
+
+
+def test_tts_audio_sink_matches_oracle_decode():
+    """The TTS server's consumer of decode_step (moshi-server/src/tts.rs:512-560, 917-929): delay gate, Pcm and
+    PcmMessagePack framing, chunked decode of a finished token matrix -- against the oracle's decode_step."""
+    import torch
+    from dsm_b200 import _lib, api
+    from dsm_b200._lib import check, ptr
+    from oracle.mimi import Mimi as OMimi
+    lib = _lib.load()
+    mspec = tiny_mimi()
+    mw = mimi_weights(mspec, seed=0, layer_scale=0.5, decoder=True)
+    steps, delay_t, delay_a = 9, 3, 2
+    rng = np.random.default_rng(2)
+    codes = rng.integers(0, mspec.bins, (mspec.n_q, steps)).astype(np.uint32)
+
+    def sink(fmt):
+        m = api.Mimi(mspec, mw, 1, encoder=False, decoder=True)
+        h = C.c_void_p()
+        check(lib.dsm_tts_sink_create(m._h, delay_t, delay_a, fmt, C.byref(h)))
+        return m, h
+
+    o = OMimi(mspec, mw, 1, decoder=True)
+    want = []
+    for t in range(delay_t + delay_a, steps):
+        pcm = o.decode_step(torch.from_numpy(codes[:, t].astype(np.int64)).view(1, -1, 1), None)
+        want.append(pcm.reshape(-1).numpy())
+    for fmt in (0, 1):
+        m, h = sink(fmt)
+        buf = (C.c_uint8 * 16384)()
+        n = C.c_size_t(0)
+        got = []
+        for t in range(steps):
+            frame = np.ascontiguousarray(codes[:, t])
+            check(lib.dsm_tts_sink_push(h, ptr(frame) if t != 1 else None, t, buf, 16384, C.byref(n)))
+            if t < delay_t + delay_a:
+                assert n.value == 0
+                continue
+            raw = bytes(buf[:n.value])
+            if fmt == 0:
+                assert len(raw) == 1920 * 4
+                got.append(np.frombuffer(raw, "<f4"))
+            else:
+                msg = msgpack.unpackb(raw)
+                assert msg["type"] == "Audio" and len(msg["pcm"]) == 1920
+                got.append(np.asarray(msg["pcm"], np.float32))
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert np.abs(g - w).max() / (np.abs(w).max() + 1e-9) < 1e-4
+        lib.dsm_tts_sink_destroy(h)
+    # the chunked decode of the whole matrix from a fresh state (tts.rs:917-929)
+    m, h = sink(0)
+    pcm_all = np.zeros(steps * 1920, np.float32)
+    check(lib.dsm_tts_sink_decode_all(h, ptr(np.ascontiguousarray(codes)), steps, ptr(pcm_all)))
+    o2 = OMimi(mspec, mw, 1, decoder=True)
+    ref = np.concatenate([o2.decode_step(torch.from_numpy(codes[:, t].astype(np.int64)).view(1, -1, 1), None).reshape(-1).numpy()
+                          for t in range(steps)])
+    assert np.abs(pcm_all - ref).max() / np.abs(ref).max() < 1e-4
+    lib.dsm_tts_sink_destroy(h)
