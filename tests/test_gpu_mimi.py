@@ -124,3 +124,34 @@ def test_shape_errors_are_reported_not_fatal():
     with pytest.raises(DsmError) as e:
         api.Mimi(spec, w, 2, decoder=False)
     assert e.value.code == -6
+
+
+def test_v0_1_codec_ring_full_and_wrapped():
+    """Mimi v0_1 at its real widths with the 250-slot codec rings (encoder AND decoder transformer) full and wrapped:
+    135 frames = 270 positions.  Codes of every frame, and the decoded audio of every frame, against the oracle."""
+    import os
+    torch.set_num_threads(os.cpu_count() or 8)
+    spec, b, frames = MimiSpec(), 2, 135
+    g, o = _pair(spec, b, encoder=True, decoder=True)
+    audio = synth_audio(b, frames)
+    rng = np.random.default_rng(3)
+    same = 0
+    worst_lat = worst_pcm = 0.0
+    for i in range(frames):
+        m = None if i % 50 != 49 else np.array([1, 0], bool)            # a few masked steps on the way
+        pcm = frame(audio, i)
+        oc = o.encode_step(torch.from_numpy(pcm).unsqueeze(1), m)[:, :, 0].numpy()
+        gc = g.encode_step(pcm, m)
+        a = active(m, b)
+        same += int((gc.astype(np.int64)[a] == oc[a]).all(axis=1).sum())
+        if i >= 125:
+            worst_lat = max(worst_lat, rel_err(g.last_latent()[a], o._last_latent[a]))
+        codes = rng.integers(0, spec.bins, (b, spec.n_q)).astype(np.uint32)
+        op = o.decode_step(torch.from_numpy(codes.astype(np.int64)).unsqueeze(-1), m)[:, 0].numpy()
+        gp = g.decode_step(codes, m)
+        if i >= 125:
+            worst_pcm = max(worst_pcm, rel_err(gp[a], op[a]))
+    total = frames * b - len(range(49, frames, 50))
+    print(f"v0_1 ring 250 wrapped: codes identical {same}/{total}, latent rel {worst_lat:.2e}, pcm rel {worst_pcm:.2e}")
+    assert same >= 0.995 * total
+    assert worst_lat < 1e-4 and worst_pcm < 1e-4
