@@ -50,6 +50,13 @@ void launch_ring_debug(const RingState& rs, const uint8_t* mask, int B, int t, i
 void launch_init_conv(const float* pcm, const float* state, int S, const float* w /*[C,k]*/, const float* bias,
                       int B, int T, int C, int k, float* out_raw, RowMap raw_map, float* out_act, RowMap act_map,
                       cudaStream_t st);
+// SEANet encoder stage 1 in one kernel (seanet_fused.cu): init conv -> resnet block -> ELU.  x1 is the k3 conv's input
+// buffer [B][2 + T][64] (head rows read as left context, this frame's last two ELU'd rows written behind them);
+// out_act / out_map address the ELU'd block output rows (b, t).
+bool seanet_stage1_supported(int c0, int k0, int c1_hidden, int k1, int k2, int T);
+void launch_seanet_stage1(const float* pcm, const float* state0, const float* w0b /*[64][8]: 7 taps + bias*/, const float* w1t,
+                          const float* b1, const float* w2t, const float* b2, float* x1, long long x1_stride_b, float* out_act,
+                          RowMap out_map, int B, int T, cudaStream_t st);
 // Last decoder conv (C_out = 1): pcm[b, t] = bias + sum_{j,ci} w[j*C+ci] * x[b, t+j, ci] (x already ELU'd).
 void launch_final_conv(const float* x, RowMap x_map /*row = (b, t)*/, const float* w /*[k*C]*/, const float* bias,
                        int B, int T, int C, int k, float* pcm, cudaStream_t st);
@@ -93,6 +100,14 @@ bool rvq_fused_supported(int bins, int qdim);
 void launch_rvq_fused(const float* embT, const float* c2, const float* emb, const float* resid, int B, int n_q, int bins,
                       int qdim, uint32_t* codes, cudaStream_t st);
 // decode: out[b, :] = sum_q E_q[codes[b,q], :] over q in [q0, q1)  (quantization.rs:231-248)
+// Grouped RVQ encode (rvq_gram.cu): Gram table E_p E_q^T [bins][bins] (built once), and the argmin chain of one group
+// of g <= DSM_RVQ_MAX_GROUP codebooks over scores [B][g][bins] of the group's entry residual.
+constexpr int DSM_RVQ_MAX_GROUP = 8;
+void launch_rvq_gram_table(const float* Ep, const float* Eq, int bins, int qd, float* G, cudaStream_t st);
+bool rvq_chain_supported(int bins, int g);
+void launch_rvq_chain(const float* scores, int B, int g, int bins, const float* gram, const float* emb /*[g][bins][qd]*/, int qd,
+                      float* residual, long long res_stride, uint32_t* codes, int n_q, int q0, __nv_bfloat16* planes,
+                      long long plane_stride, cudaStream_t st);
 void launch_rvq_gather_sum(const uint32_t* codes, int n_q, int q0, int q1, const float* embeddings /*[n_q][bins][qdim]*/,
                            int bins, int qdim, int B, float* out, cudaStream_t st);
 // depthwise conv-transpose k=2s (ConvTrUpsample1d, conv.rs:558-606), one input frame -> s frames,

@@ -287,10 +287,18 @@ static void build_seanet(const SeanetBuild& sb, const std::vector<SeanetLayer>& 
       keff[i] = L[i].k, seff[i] = L[i].stride, S[i] = L[i].k - L[i].stride, N[i] = L[i].cout, T[i + 1] = T[i] / L[i].stride;
     }
   }
+  // Encoder stage 1 (init conv + first resnet block) as one CUDA-core kernel (seanet_fused.cu) instead of an init
+  // conv and two short-K GEMMs.  Opt-in (DSM_SEANET_FUSED1=1) until it beats the layer-by-layer path.
+  static const bool fuse1_on = [] { const char* e = getenv("DSM_SEANET_FUSED1"); return e && e[0] == '1'; }();
+  const bool fuse1 = fuse1_on && !first_in && n > 3 && L[1].res == 1 && L[2].res == 2 && L[1].elu_in && L[2].elu_in && L[3].elu_in &&
+                     !L[1].tr && !L[2].tr && L[1].cin == L[0].cout && L[2].cout == L[0].cout &&
+                     seanet_stage1_supported(L[0].cout, L[0].k, L[1].cout, L[1].k, L[2].k, T0);
+  float *f1_w0 = nullptr, *f1_w1t = nullptr, *f1_b1 = nullptr, *f1_w2t = nullptr;
   // input buffers
   std::vector<float*> X(n, nullptr);
   for (int i = 0; i < n; ++i) {
     if (i == 0) X[i] = first_in;
+    else if (fuse1 && i == 2) continue;            // the block's hidden activation never leaves shared memory
     else X[i] = arena.alloc<float>((size_t)B * (S[i] + T[i]) * L[i].cin);
     if (X[i] && S[i] > 0) {
       const long long sb_ = (long long)(S[i] + T[i]) * L[i].cin;
@@ -326,6 +334,26 @@ static void build_seanet(const SeanetBuild& sb, const std::vector<SeanetLayer>& 
         dBias = arena.upload(bias);
       }
     }
+    if (fuse1 && i < 2) {
+      // weights in the fused kernel's layouts: w0 [64][7] as is, w1 [32][192] -> [192][32]
+      if (i == 0) {
+        std::vector<float> bias0 = (*sb.get)(y.wname + ".bias", y.cout, 0.05f, 0.f);
+        std::vector<float> t((size_t)y.cout * 8, 0.f);             // [64][8]: the 7 taps, then the bias
+        for (int co = 0; co < y.cout; ++co) {
+          for (int q = 0; q < y.k; ++q) t[(size_t)co * 8 + q] = hW[(size_t)co * y.k + q];
+          t[(size_t)co * 8 + 7] = bias0[co];
+        }
+        f1_w0 = arena.upload(t);
+      }
+      else {
+        const int K = keff[i] * y.cin;
+        std::vector<float> t((size_t)K * y.cout);
+        for (int nn = 0; nn < y.cout; ++nn)
+          for (int kk = 0; kk < K; ++kk) t[(size_t)kk * y.cout + nn] = hW[(size_t)nn * K + kk];
+        f1_w1t = arena.upload(t), f1_b1 = dBias;
+      }
+      continue;
+    }
     // ---- outputs ----
     float* out_act = nullptr;
     float* out_raw = nullptr;
@@ -345,6 +373,20 @@ static void build_seanet(const SeanetBuild& sb, const std::vector<SeanetLayer>& 
       }
     } else if (final_out) {
       out_raw = final_out, raw_map = final_map;
+    }
+    if (fuse1 && i == 2) {
+      std::vector<float> t((size_t)y.cin * y.cout);               // w2 [64][32] -> [32][64]
+      for (int nn = 0; nn < y.cout; ++nn)
+        for (int kk = 0; kk < y.cin; ++kk) t[(size_t)kk * y.cout + nn] = hW[(size_t)nn * y.cin + kk];
+      f1_w2t = arena.upload(t);
+      DSM_CHECK(out_act && !out_raw, DSM_ERR_UNSUPPORTED, "fused stage 1 expects an activated consumer");
+      float* x1 = X[1];
+      const long long x1_stride = (long long)(S[1] + T[1]) * L[1].cin;
+      const int T_in = T[0];
+      sb.plan->push_back([=](cudaStream_t st) {
+        launch_seanet_stage1(pcm_in, state0, f1_w0, f1_w1t, f1_b1, f1_w2t, dBias, x1, x1_stride, out_act, act_map, B, T_in, st);
+      });
+      continue;
     }
     const float* res = nullptr;
     RowMap res_map{1, 0, 0};
@@ -553,8 +595,51 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
           for (int d = 0; d < qd; ++d) t[((size_t)q * qd + d) * bins + j] = emb_host[((size_t)q * bins + j) * qd + d];
       embT = arena.upload(t);
     }
-    std::vector<std::shared_ptr<CodecGemm>> g_score(fused ? 0 : nq);
-    for (int q = 0; q < (fused ? 0 : nq); ++q) {
+    // Grouped encode (rvq_gram.cu): one score GEMM + one argmin-chain kernel per group of DSM_RVQ_GROUP codebooks
+    // (default 8; 1 = one GEMM + select per codebook, the reference's association).
+    static const int rvq_group = [] {
+      const char* e = getenv("DSM_RVQ_GROUP");
+      return std::min(std::max(e ? atoi(e) : DSM_RVQ_MAX_GROUP, 1), DSM_RVQ_MAX_GROUP);
+    }();
+    const bool grouped = !fused && rvq_group > 1 && rvq_chain_supported(bins, rvq_group);
+    if (grouped) {
+      struct Group { int q0, g, off; std::shared_ptr<CodecGemm> gemm; float* gram; };
+      std::vector<Group> groups;
+      groups.push_back(Group{0, 1, 0, nullptr, nullptr});                    // rvq_first: its own projected input
+      for (int q = 1; q < nq; q += rvq_group) groups.push_back(Group{q, std::min(rvq_group, nq - q), qd, nullptr, nullptr});
+      float* gscores = arena.alloc<float>((size_t)Bc * rvq_group * bins);
+      for (Group& G : groups) {
+        GemmParams s;
+        s.A = resid + G.off, s.a_map = RowMap{1, (long long)2 * qd, (long long)2 * qd};
+        s.M = Bc, s.N = G.g * bins, s.K = qd;
+        s.bias = c2_all + (size_t)G.q0 * bins, s.neg = 1;     // |e|^2/2 - r.e for every codebook of the group
+        s.out_raw = gscores, s.o_map = dense_rows(1, G.g * bins);
+        if (resid_pl) s.a_planes = resid_pl + G.off, s.a_plane_stride = RP;
+        std::vector<float> Eg(emb_host.begin() + (size_t)G.q0 * bins * qd, emb_host.begin() + (size_t)(G.q0 + G.g) * bins * qd);
+        G.gemm = make_codec_gemm(arena, s, Eg, wsp);
+        if (G.g > 1) {
+          const size_t tbl = (size_t)bins * bins;
+          G.gram = arena.alloc<float>((size_t)G.g * (G.g - 1) / 2 * tbl, false);
+          for (int p = 0; p < G.g; ++p)
+            for (int q = p + 1; q < G.g; ++q)
+              launch_rvq_gram_table(emb_all + (size_t)(G.q0 + p) * bins * qd, emb_all + (size_t)(G.q0 + q) * bins * qd, bins, qd,
+                                    G.gram + (size_t)(p * G.g - p * (p + 1) / 2 + (q - p - 1)) * tbl, stream);
+        }
+      }
+      float* res = resid;
+      float* emb = emb_all;
+      uint32_t* codes = d_codes;
+      enc_plan.push_back([=](cudaStream_t st) {
+        run_codec_gemm(*g_proj, st);
+        for (const Group& G : groups) {
+          run_codec_gemm(*G.gemm, st);
+          launch_rvq_chain(gscores, Bc, G.g, bins, G.gram, emb + (size_t)G.q0 * bins * qd, qd, res + G.off, 2 * qd, codes, nq, G.q0,
+                           resid_pl ? resid_pl + G.off : nullptr, RP, st);
+        }
+      });
+    }
+    std::vector<std::shared_ptr<CodecGemm>> g_score(fused || grouped ? 0 : nq);
+    for (int q = 0; q < (fused || grouped ? 0 : nq); ++q) {
       GemmParams s;
       s.A = resid + (q == 0 ? 0 : qd), s.a_map = RowMap{1, (long long)2 * qd, (long long)2 * qd};
       s.M = Bc, s.N = bins, s.K = qd;
@@ -574,7 +659,7 @@ void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {
         run_codec_gemm(*g_proj, st);
         launch_rvq_fused(embT, c2p, emb, res, Bc, nq, bins, qd, codes, st);
       });
-    } else
+    } else if (!grouped)
     enc_plan.push_back([=](cudaStream_t st) {
       run_codec_gemm(*g_proj, st);
       for (int q = 0; q < nq; ++q) {
