@@ -247,7 +247,9 @@ struct SchedImpl {
   }
 
   // ---- pre_process (batched_asr.rs:527-653): one frame per slot with data into batch[buf], mask, resets, markers ----
-  Gathered gather(SchedDevice& d, std::vector<SchedOut>* outs, bool to_queues) {
+  // in_flight: steps begun but not yet counted in d.step_idx (the pipelined loop gathers frame t+1 before it collects
+  // step t); frames they consumed are already in total_popped(), so a marker's due step must count them as well.
+  Gathered gather(SchedDevice& d, std::vector<SchedOut>* outs, bool to_queues, int in_flight = 0) {
     const long long t0 = now_ns();
     Gathered g;
     g.buf = d.cur;
@@ -271,7 +273,7 @@ struct SchedImpl {
         // fires once the model has consumed what was queued ahead of the marker plus the text delay (:577-585)
         const uint64_t consumed = sl.pcm.total_popped();
         const long long ahead = m.pushed_at > consumed ? (long long)((m.pushed_at - consumed) / DSM_FRAME_SIZE) : 0;
-        d.markers.push(SchedMarker{cid, d.index * d.B + i, d.step_idx + d.delay + ahead, m.id});
+        d.markers.push(SchedMarker{cid, d.index * d.B + i, d.step_idx + in_flight + d.delay + ahead, m.id});
       }
       float* dst = batch + (size_t)i * DSM_FRAME_SIZE;
       if (sl.pcm.pop(dst, DSM_FRAME_SIZE)) {
@@ -375,7 +377,7 @@ struct SchedImpl {
     try {
       while (running.load(std::memory_order_acquire)) {
         d.stats.ticks += 1;
-        Gathered g = gather(d, nullptr, true);          // into batch[d.cur], which no step in flight reads
+        Gathered g = gather(d, nullptr, true, pending ? 1 : 0);   // into batch[d.cur], which no step in flight reads
         if (pending) {
           const long long t0 = now_ns();
           if (d.asr) d.asr->step_end(d.tokens.data());

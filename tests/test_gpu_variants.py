@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 VARIANTS = [
     ({"DSM_TC6_SPLITK": "0"}, ["tests/test_gpu_codec_gemm.py", "tests/test_gpu_mimi.py"]),
     ({"DSM_CODEC_PRESPLIT": "0"}, ["tests/test_gpu_mimi.py"]),
-    ({"DSM_SEANET_FUSED1": "1"}, ["tests/test_gpu_mimi.py"]),
+    ({"DSM_SEANET_FUSED1": "0"}, ["tests/test_gpu_mimi.py"]),
     ({"DSM_RVQ_GROUP": "1"}, ["tests/test_gpu_mimi.py", "tests/test_gpu_real_audio.py"]),
     ({"DSM_RVQ_GROUP": "3"}, ["tests/test_gpu_mimi.py"]),
     ({"DSM_RVQ_FUSED_MAX": "512"}, ["tests/test_gpu_mimi.py", "tests/test_gpu_real_audio.py"]),
