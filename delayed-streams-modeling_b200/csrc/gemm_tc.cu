@@ -1,4 +1,5 @@
 #include "gemm_tc.cuh"
+#include "runtime.cuh"
 
 #include <mutex>
 
@@ -384,10 +385,13 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
   // 131 MB of partial planes (22.1 vs 23.2 ms); it is neutral for QKV / text head there, and at 1,024 streams it costs
   // 0.9 ms when it leaves QKV with 96 CTAs.  Hence: wide when the narrow grid is about a wave or more AND either the
   // wide grid still fills the SMs or the narrow one would not have.
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  const long long sms = sm_budget(SmBranch::LM, cur_dev);     // all SMs, or the LM partition under DSM_SM_SPLIT
   const long long narrow_tiles = (long long)ceil_div(n_rows, TC_BN) * ceil_div(M, 256);
   const long long wide_tiles = (long long)ceil_div(n_rows, 2 * TC_BN) * ceil_div(M, 256);
   const bool wide = mode != TC_GATE_BF16 && M > 256 && n_rows >= 2 * TC_BN && narrow_tiles >= 100 &&
-                    (wide_tiles >= 148 || narrow_tiles < 148);
+                    (wide_tiles >= sms || narrow_tiles < sms);
   g.nacc = (mode == TC_GATE_BF16 || wide) ? 2 : 1;
   const int n_tiles = ceil_div(n_rows, TC_BN * (mode == TC_GATE_BF16 ? 1 : g.nacc));
   // Stream tile: as wide as the batch allows.  Every CTA must pull its W slab AND its X slab through
@@ -397,7 +401,7 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
   // The gate pair holds two accumulators: 128 streams per tile while that is what covers the SMs (256 streams: 88
   // CTAs instead of 44), 256 -- all 512 TMEM columns, twice the MMAs per operand byte -- once the batch fills them
   const long long gate_tiles_256 = (long long)ceil_div(n_rows, TC_BN) * ceil_div(M, 256);
-  g.bmx = M <= 64 ? 64 : (M <= 128 ? 128 : ((mode == TC_GATE_BF16 && gate_tiles_256 < 148) ? 128 : 256));
+  g.bmx = M <= 64 ? 64 : (M <= 128 ? 128 : ((mode == TC_GATE_BF16 && gate_tiles_256 < sms) ? 128 : 256));
   // DSM_TC_MAXSPLIT caps split-K (1 = no split: A/B of the partial-sum path)
   static const int env_split = [] { const char* e = getenv("DSM_TC_MAXSPLIT"); return e ? std::min(atoi(e), TC_MAX_SPLIT) : TC_MAX_SPLIT; }();
   g.split_k = 1;
@@ -408,7 +412,7 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
     const int kb = K / TC_BK;
     const long long base = (long long)n_tiles * ceil_div(M, g.bmx);
     double best = 0.0;
-    const long long wave = 148;
+    const long long wave = sms;
     // (measured at 2,000 streams: out-proj / MLP-out with 128 tiles and no split 140 us per launch, with 8 splits and
     // their 131 MB of partial planes 89 us -- the split stays whenever the tiles alone do not fill the SMs)
     for (int s = 1; s <= (base >= wave ? 1 : env_split); ++s) {

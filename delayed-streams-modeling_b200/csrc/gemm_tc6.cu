@@ -720,9 +720,16 @@ static void launch6(const Tc6Gemm& g, cudaStream_t st) {
   p.out_raw = g.ep.out_raw, p.o_map = g.ep.o_map, p.out_act = g.ep.out_act, p.e_map = g.ep.e_map;
   p.out_pl = g.ep.out_planes, p.pl_map = g.ep.p_map, p.pl_stride = g.ep.out_plane_stride;
   const long long tiles = (long long)p.m_tiles * p.n_groups * g.split_k;
-  const int grid = (int)std::min<long long>(tiles, 148);
+  const int grid = (int)std::min<long long>(tiles, g.sms);
   launch_k(kern, grid, T6_THREADS, C::SMEM, st, g.map_a, g.map_w, p);
   check_launch("tc6_gemm");
+}
+
+// SMs the codec branch may use: all of them, or its partition under DSM_SM_SPLIT (runtime.cu)
+static int codec_sms() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return sm_budget(SmBranch::CODEC, d);
 }
 
 bool tc6_supported(const GemmParams& g) {
@@ -796,7 +803,9 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes,
   constexpr int max_tile_n = 64;
   // pre-split A: one column sub-tile per CTA keeps the W ring as deep (in k-blocks) as the operand ring
   int nj = std::max(1, std::min(n_sub, std::min(g.a_planes ? 64 : 128, max_tile_n) / t.bn));
-  while (nj > 1 && m_tiles * ceil_div(n_sub, nj) < 148) nj = (nj + 1) / 2;
+  const int sms = codec_sms();
+  t.sms = sms;
+  while (nj > 1 && m_tiles * ceil_div(n_sub, nj) < sms) nj = (nj + 1) / 2;
   t.nj = nj;
   // TMEM: 512 accumulator columns, or 320 when the A planes live in tensor memory (f32-A variant).  Two tile
   // buffers when they fit with at least one main accumulator beside the correction accumulator; long K loops
@@ -821,8 +830,8 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes,
     // turns it off; only considered where >= 6 k-blocks remain per split.
     static const bool splitk_on = [] { const char* e = getenv("DSM_TC6_SPLITK"); return !(e && e[0] == '0'); }();
     // (the last-arrival reduce path does not write plane outputs: such GEMMs never split)
-    if (splitk_on && wsp.ws && tiles <= 74 && num_kb >= 16 && !g.out_planes) {
-      S = (int)std::max<long long>(1, std::min<long long>(148 / tiles, num_kb / 6));
+    if (splitk_on && wsp.ws && tiles <= sms / 2 && num_kb >= 16 && !g.out_planes) {
+      S = (int)std::max<long long>(1, std::min<long long>(sms / tiles, num_kb / 6));
       const int per = ceil_div(num_kb, S);
       S = ceil_div(num_kb, per);
       const size_t need = (size_t)tiles * S * T6_BM * nj * t.bn * sizeof(float);

@@ -25,6 +25,7 @@ struct Tc6Gemm {
   CUtensorMap map_w;   // bf16 [3][N][K] pre-split weight planes
   int K = 0, N = 0, T_out = 0, B = 0;
   int t_sub = 0, b_sub = 0, bn = 0, nj = 0, pm = 1, split_k = 1, acc_bufs = 2;
+  int sms = 148;       // persistent grid size cap: the SMs of the branch's partition (runtime.cuh)
   bool presplit = false;   // A arrives as bf16 planes (GemmParams::a_planes): TMA feeds the operand buffers directly
   float* ws = nullptr;
   int* counters = nullptr;

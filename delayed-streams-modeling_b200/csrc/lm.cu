@@ -42,7 +42,7 @@ LmImpl::LmImpl(const dsm_lm_spec& sp, const dsm_weights* w, int dev, int batch, 
   hidden = sp.dim_feedforward == 4 * D ? 11 * D / 4 : 2 * sp.dim_feedforward / 3;   // batched_transformer.rs:153-157
   DSM_CHECK(hidden % 16 == 0, DSM_ERR_UNSUPPORTED, "gated hidden size %d must be a multiple of 16", hidden);
   DSM_CUDA(cudaSetDevice(device));
-  DSM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  stream = create_branch_stream(SmBranch::LM, device);
   WeightTable wt(w);
   const bool random = (w == nullptr);
 

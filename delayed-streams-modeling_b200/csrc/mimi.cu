@@ -440,7 +440,7 @@ MimiImpl::MimiImpl(const dsm_mimi_spec& sp, const dsm_weights* w, int dev, int b
             "mimi spec outside the v0_1 family (n_q=%d qdim=%d dim=%d)", sp.n_q, sp.qdim, sp.dim);
   DSM_CHECK(sp.with_encoder || sp.with_decoder, DSM_ERR_INVALID_ARG, "mimi spec enables neither encoder nor decoder");
   DSM_CUDA(cudaSetDevice(device));
-  DSM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  stream = create_branch_stream(SmBranch::CODEC, device);
   WeightTable wt(w);
   const bool random = (w == nullptr);
   // Tensor getter: from the table (either of `a|b` alternative names), or seeded host-side random init

@@ -1,9 +1,14 @@
 #include "runtime.cuh"
 
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
 
 namespace dsm {
 
@@ -228,6 +233,90 @@ bool pdl_enabled() {
   // So it is opt-in (DSM_PDL=1).
   static const bool on = [] { const char* e = getenv("DSM_PDL"); return e && e[0] == '1'; }();
   return on;
+}
+
+// ---- SM partitions ------------------------------------------------------------------------------
+namespace {
+struct SmPartition {
+  bool ok = false;
+  CUgreenCtx ctx[2] = {nullptr, nullptr};
+  int sms[2] = {0, 0};
+};
+template <typename F>
+F driver_fn(const char* name) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+    fail(DSM_ERR_UNSUPPORTED, "driver entry point %s is not available (DSM_SM_SPLIT needs CUDA green contexts)", name);
+  return reinterpret_cast<F>(p);
+}
+int sm_split_request() {
+  static const int n = [] { const char* e = getenv("DSM_SM_SPLIT"); return e ? atoi(e) : 0; }();
+  return n;
+}
+// "104s": soft split -- the LM branch is confined to its partition, the codec branch may use every SM (it keeps the
+// rest to itself and borrows the LM's SMs whenever the LM's latency-bound GEMMs leave them idle)
+bool sm_split_soft() {
+  static const bool soft = [] { const char* e = getenv("DSM_SM_SPLIT"); return e && strchr(e, 's') != nullptr; }();
+  return soft;
+}
+SmPartition& sm_partition(int device) {
+  static std::mutex mu;
+  static std::map<int, SmPartition> parts;
+  std::lock_guard<std::mutex> l(mu);
+  SmPartition& P = parts[device];
+  if (P.ok) return P;
+  DSM_CUDA(cudaSetDevice(device));
+  DSM_CUDA(cudaFree(nullptr));                 // the primary context must exist
+  auto dev_get = driver_fn<CUresult (*)(CUdevice*, int)>("cuDeviceGet");
+  auto get_res = driver_fn<CUresult (*)(CUdevice, CUdevResource*, CUdevResourceType)>("cuDeviceGetDevResource");
+  auto split = driver_fn<CUresult (*)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int)>(
+      "cuDevSmResourceSplitByCount");
+  auto gen = driver_fn<CUresult (*)(CUdevResourceDesc*, CUdevResource*, unsigned int)>("cuDevResourceGenerateDesc");
+  auto create = driver_fn<CUresult (*)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int)>("cuGreenCtxCreate");
+  auto chk = [](CUresult r, const char* what) {
+    if (r != CUDA_SUCCESS) fail(DSM_ERR_CUDA, "%s failed with CUresult %d", what, (int)r);
+  };
+  CUdevice dev;
+  chk(dev_get(&dev, device), "cuDeviceGet");
+  CUdevResource all, part[1], rest;
+  chk(get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM), "cuDeviceGetDevResource");
+  unsigned int groups = 1;
+  chk(split(part, &groups, &all, &rest, 0, (unsigned)sm_split_request()), "cuDevSmResourceSplitByCount");
+  DSM_CHECK(groups == 1 && rest.sm.smCount > 0, DSM_ERR_INVALID_ARG, "DSM_SM_SPLIT=%d leaves no SMs for the codec branch (%u in all)",
+            sm_split_request(), all.sm.smCount);
+  CUdevResource* src[2] = {&part[0], &rest};
+  for (int i = 0; i < 2; ++i) {
+    CUdevResourceDesc desc;
+    chk(gen(&desc, src[i], 1), "cuDevResourceGenerateDesc");
+    chk(create(&P.ctx[i], desc, dev, CU_GREEN_CTX_DEFAULT_STREAM), "cuGreenCtxCreate");
+    P.sms[i] = (int)src[i]->sm.smCount;
+  }
+  fprintf(stderr, "dsm: device %d split into %d SMs (LM branch) + %d SMs (codec branch)\n", device, P.sms[0], P.sms[1]);
+  P.ok = true;
+  return P;
+}
+}  // namespace
+
+bool sm_split_enabled() { return sm_split_request() > 0; }
+
+int sm_budget(SmBranch which, int device) {
+  if (!sm_split_enabled() || (which == SmBranch::CODEC && sm_split_soft())) return 148;
+  return sm_partition(device).sms[which == SmBranch::LM ? 0 : 1];
+}
+
+cudaStream_t create_branch_stream(SmBranch which, int device) {
+  cudaStream_t st = nullptr;
+  if (!sm_split_enabled() || (which == SmBranch::CODEC && sm_split_soft())) {
+    DSM_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    return st;
+  }
+  SmPartition& P = sm_partition(device);
+  auto mk = driver_fn<CUresult (*)(CUstream*, CUgreenCtx, unsigned int, int)>("cuGreenCtxStreamCreate");
+  CUstream cs = nullptr;
+  const CUresult r = mk(&cs, P.ctx[which == SmBranch::LM ? 0 : 1], CU_STREAM_NON_BLOCKING, 0);
+  if (r != CUDA_SUCCESS) fail(DSM_ERR_CUDA, "cuGreenCtxStreamCreate failed with CUresult %d", (int)r);
+  return reinterpret_cast<cudaStream_t>(cs);
 }
 
 bool graphs_enabled() {

@@ -86,6 +86,14 @@ class GraphExec {
   long long launches_ = 0;  // kernel launches inside one replay
 };
 
+// SM partitioning (CUDA green contexts), opt-in: DSM_SM_SPLIT=<n> gives the LM branch of the frame graph n SMs
+// (rounded to the hardware's granularity) and the codec branch the rest, so that the HBM-bound attention and the
+// tensor / FMA-bound codec kernels run side by side instead of queueing for whole SMs.  The branch streams are then
+// created on the partitions and the persistent GEMM grids are sized to them.
+enum class SmBranch { LM, CODEC };
+bool sm_split_enabled();
+int sm_budget(SmBranch which, int device);                       // SMs of the branch's partition (all of them when off)
+cudaStream_t create_branch_stream(SmBranch which, int device);   // a non-blocking stream on the branch's partition
 bool graphs_enabled();  // false when DSM_NO_GRAPH=1 or dsm_set_graphs(0)
 void set_graphs_enabled(int v);
 const std::string& last_error();
