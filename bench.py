@@ -496,6 +496,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
 
+    sm_part = asr.sm_partition() if is_asr else (0, 0)
     # ---- optional: largest batch that fits in HBM and keeps p99 <= 80 ms ----
     live = None
     if args.live_sweep and world == 1:
@@ -550,6 +551,12 @@ def run_ours(args):
                         "d2h_bytes_per_step": (B * 4 + 4 * lspec.extra_heads_num * B) if is_asr else
                         (B * FRAME * 4 if args.workload == "decode" else B * 128)},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        if is_asr:
+            lm_sms, codec_sms = sm_part
+            line["config"]["sm_partition"] = ({"lm_sms": lm_sms, "codec_sms": codec_sms,
+                                               "how": "the LM and codec branches of the frame graph run on disjoint SM sets (CUDA green contexts); "
+                                                      "roofline.frac / lm_step_ms are measured inside the LM partition"}
+                                              if lm_sms else None)
         if live is not None:
             line["live_streams_max"] = live["live_streams_max"]
             line["live_sweep"] = live

@@ -160,6 +160,7 @@ SIGNATURES = {
     "dsm_asr_delay_in_tokens": (C.c_int32, [_P]),
     "dsm_asr_last_logits": (C.c_int32, [_P, _P]),
     "dsm_asr_last_step_ms": (C.c_int32, [_P, C.POINTER(C.c_float * 3)]),
+    "dsm_asr_sm_partition": (C.c_int32, [_P, C.POINTER(C.c_int32 * 2)]),
     "dsm_weights_open": (C.c_int32, [C.c_char_p, C.POINTER(_P)]),
     "dsm_weight_file_table": (C.POINTER(Weights), [_P]),
     "dsm_weight_file_metadata": (C.c_int64, [_P, C.c_char_p, C.c_char_p, C.c_size_t]),

@@ -289,6 +289,12 @@ class AsrState:
         check(self._lib.dsm_asr_last_step_ms(self._h, C.byref(arr)))
         return arr[0], arr[1], arr[2]
 
+    def sm_partition(self) -> Tuple[int, int]:
+        """(SMs of the LM branch, SMs of the codec branch); (0, 0) when the branches share the device."""
+        arr = (C.c_int32 * 2)()
+        check(self._lib.dsm_asr_sm_partition(self._h, C.byref(arr)))
+        return arr[0], arr[1]
+
     def reset(self):
         check(self._lib.dsm_asr_reset(self._h))
 

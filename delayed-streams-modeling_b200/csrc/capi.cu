@@ -490,5 +490,11 @@ dsm_status dsm_asr_last_step_ms(dsm_asr* h, float out[3]) {
     for (int i = 0; i < 3; ++i) out[i] = h->impl->last_ms[i];
   });
 }
+dsm_status dsm_asr_sm_partition(const dsm_asr* h, int32_t out[2]) {
+  return guarded([&] {
+    REQUIRE(h && out, "handle and out are required");
+    out[0] = h->impl->sm_split_lm, out[1] = h->impl->sm_split_codec;
+  });
+}
 
 }  // extern "C"

@@ -1,5 +1,4 @@
 #include "gemm_tc.cuh"
-#include "runtime.cuh"
 
 #include <mutex>
 
@@ -372,7 +371,7 @@ static void launch_tc(const TcGemm& g, cudaStream_t st) {
 }
 
 void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, int M, int N, int K, int mode,
-                     float* out_f32, __nv_bfloat16* out_bf16) {
+                     float* out_f32, __nv_bfloat16* out_bf16, int sms_budget) {
   DSM_CHECK(tc_gemm_supported(M, N, K, mode), DSM_ERR_UNSUPPORTED, "tc_gemm: unsupported problem M=%d N=%d K=%d mode=%d", M, N,
             K, mode);
   g.M = M, g.N = N, g.K = K, g.mode = mode, g.out_f32 = out_f32, g.out_bf16 = out_bf16;
@@ -385,9 +384,7 @@ void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, 
   // 131 MB of partial planes (22.1 vs 23.2 ms); it is neutral for QKV / text head there, and at 1,024 streams it costs
   // 0.9 ms when it leaves QKV with 96 CTAs.  Hence: wide when the narrow grid is about a wave or more AND either the
   // wide grid still fills the SMs or the narrow one would not have.
-  int cur_dev = 0;
-  cudaGetDevice(&cur_dev);
-  const long long sms = sm_budget(SmBranch::LM, cur_dev);     // all SMs, or the LM partition under DSM_SM_SPLIT
+  const long long sms = sms_budget;     // all SMs, or the LM partition of an ASR state (runtime.cuh)
   const long long narrow_tiles = (long long)ceil_div(n_rows, TC_BN) * ceil_div(M, 256);
   const long long wide_tiles = (long long)ceil_div(n_rows, 2 * TC_BN) * ceil_div(M, 256);
   const bool wide = mode != TC_GATE_BF16 && M > 256 && n_rows >= 2 * TC_BN && narrow_tiles >= 100 &&

@@ -41,8 +41,9 @@ struct TcGemm {
 };
 
 // Builds the tensor maps and picks the tile / split-K so the grid covers the 148 SMs.
+// sms_budget: the SMs the GEMM may count on (tile shape and split-K are chosen to fill them)
 void tc_gemm_prepare(TcGemm& g, const __nv_bfloat16* W, const __nv_bfloat16* X, int M, int N, int K, int mode,
-                     float* out_f32, __nv_bfloat16* out_bf16);
+                     float* out_f32, __nv_bfloat16* out_bf16, int sms_budget = 148);
 void tc_gemm_launch(const TcGemm& g, cudaStream_t st);
 void tc_reduce_partials(const TcGemm& g, cudaStream_t st);   // out (+)= sum of the partial planes, in split order
 bool tc_gemm_supported(int M, int N, int K, int mode);

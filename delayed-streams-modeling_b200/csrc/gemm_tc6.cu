@@ -725,13 +725,6 @@ static void launch6(const Tc6Gemm& g, cudaStream_t st) {
   check_launch("tc6_gemm");
 }
 
-// SMs the codec branch may use: all of them, or its partition under DSM_SM_SPLIT (runtime.cu)
-static int codec_sms() {
-  int d = 0;
-  cudaGetDevice(&d);
-  return sm_budget(SmBranch::CODEC, d);
-}
-
 bool tc6_supported(const GemmParams& g) {
   if (g.M <= 0 || g.N % 32 != 0 || g.K % 32 != 0 || g.out_bf16) return false;
   if (g.a_map.T <= 0 || g.M % g.a_map.T != 0) return false;
@@ -782,7 +775,7 @@ __nv_bfloat16* tc6_split_weights(Arena& arena, const std::vector<float>& w, int 
   return d;
 }
 
-void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes, const Tc6Workspace& wsp) {
+void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes, const Tc6Workspace& wsp, int sms) {
   DSM_CHECK(tc6_supported(g), DSM_ERR_UNSUPPORTED, "tc6_gemm: unsupported problem M=%d N=%d K=%d", g.M, g.N, g.K);
   t.ep = g;
   t.K = g.K, t.N = g.N, t.T_out = g.a_map.T, t.B = g.M / g.a_map.T;
@@ -803,7 +796,6 @@ void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes,
   constexpr int max_tile_n = 64;
   // pre-split A: one column sub-tile per CTA keeps the W ring as deep (in k-blocks) as the operand ring
   int nj = std::max(1, std::min(n_sub, std::min(g.a_planes ? 64 : 128, max_tile_n) / t.bn));
-  const int sms = codec_sms();
   t.sms = sms;
   while (nj > 1 && m_tiles * ceil_div(n_sub, nj) < sms) nj = (nj + 1) / 2;
   t.nj = nj;

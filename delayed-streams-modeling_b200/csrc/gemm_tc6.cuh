@@ -36,7 +36,10 @@ struct Tc6Gemm {
 bool tc6_supported(const GemmParams& g);
 // Splits an f32 [N, K] weight matrix into three bf16 planes on the device ([3][N][K]).
 __nv_bfloat16* tc6_split_weights(Arena& arena, const std::vector<float>& w, int N, int K);
-void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes, const Tc6Workspace& wsp = Tc6Workspace());
+// sms: the SMs the kernel may count on (all 148, or the codec partition of an ASR state: runtime.cuh) -- it sizes the
+// persistent grid, the column grouping and the split-K.  May be called again on a prepared GEMM to re-tune it.
+void tc6_prepare(Tc6Gemm& t, const GemmParams& g, const __nv_bfloat16* w_planes, const Tc6Workspace& wsp = Tc6Workspace(),
+                 int sms = 148);
 void tc6_launch(const Tc6Gemm& t, cudaStream_t st);
 
 }  // namespace dsm

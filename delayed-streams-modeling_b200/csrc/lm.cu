@@ -42,7 +42,7 @@ LmImpl::LmImpl(const dsm_lm_spec& sp, const dsm_weights* w, int dev, int batch, 
   hidden = sp.dim_feedforward == 4 * D ? 11 * D / 4 : 2 * sp.dim_feedforward / 3;   // batched_transformer.rs:153-157
   DSM_CHECK(hidden % 16 == 0, DSM_ERR_UNSUPPORTED, "gated hidden size %d must be a multiple of 16", hidden);
   DSM_CUDA(cudaSetDevice(device));
-  stream = create_branch_stream(SmBranch::LM, device);
+  DSM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   WeightTable wt(w);
   const bool random = (w == nullptr);
 
@@ -162,15 +162,24 @@ LmImpl::LmImpl(const dsm_lm_spec& sp, const dsm_weights* w, int dev, int batch, 
     const char* e = getenv("DSM_LM_GEMM");
     use_tc = !(e && std::string(e) == "simt");
   }
+  tune_plans(148);
+  DSM_CUDA(cudaStreamSynchronize(stream));
+}
+
+// (Re)builds the GEMM launch configurations and both step plans for `sm_budget` SMs: tile shapes and split-K are
+// chosen to fill the SMs the LM branch may use -- all of them, or its partition inside an ASR state (runtime.cuh).
+void LmImpl::tune_plans(int sm_budget) {
+  const dsm_lm_spec& sp = spec;
+  sms = sm_budget;
   if (use_tc) {
     for (int l = 0; l < L; ++l) {
       Layer& y = layers[l];
-      tc_gemm_prepare(y.g_qkv, y.in_proj, xn, B, 3 * D, D, TC_STORE_F32, qkv, nullptr);
-      tc_gemm_prepare(y.g_out, y.out_proj, attn, B, D, D, TC_ACCUM_F32, x, nullptr);
-      tc_gemm_prepare(y.g_in, y.lin_in, xn, B, 2 * hidden, D, TC_GATE_BF16, nullptr, gbuf);
-      tc_gemm_prepare(y.g_down, y.lin_out, gbuf, B, D, hidden, TC_ACCUM_F32, x, nullptr);
+      tc_gemm_prepare(y.g_qkv, y.in_proj, xn, B, 3 * D, D, TC_STORE_F32, qkv, nullptr, sms);
+      tc_gemm_prepare(y.g_out, y.out_proj, attn, B, D, D, TC_ACCUM_F32, x, nullptr, sms);
+      tc_gemm_prepare(y.g_in, y.lin_in, xn, B, 2 * hidden, D, TC_GATE_BF16, nullptr, gbuf, sms);
+      tc_gemm_prepare(y.g_down, y.lin_out, gbuf, B, D, hidden, TC_ACCUM_F32, x, nullptr, sms);
     }
-    tc_gemm_prepare(g_text, text_linear, ys_bf16, B, sp.text_out_vocab_size, D, TC_STORE_F32, logits, nullptr);
+    tc_gemm_prepare(g_text, text_linear, ys_bf16, B, sp.text_out_vocab_size, D, TC_STORE_F32, logits, nullptr, sms);
     // one buffer for the split-K partial planes of all of them: each GEMM's partials are consumed by the very next
     // kernel of the stream (RMSNorm / RoPE-scatter / argmax) before the following GEMM writes its own
     std::vector<TcGemm*> all{&g_text};
@@ -178,14 +187,26 @@ LmImpl::LmImpl(const dsm_lm_spec& sp, const dsm_weights* w, int dev, int batch, 
       for (TcGemm* g : {&y.g_qkv, &y.g_out, &y.g_in, &y.g_down}) all.push_back(g);
     size_t bytes = 0;
     for (TcGemm* g : all) bytes = std::max(bytes, g->partial_bytes);
-    if (bytes) {
-      float* buf = arena.alloc<float>(bytes / sizeof(float), false);
-      for (TcGemm* g : all) g->partials = buf;
+    if (bytes > partial_buf_bytes) {
+      partial_buf = arena.alloc<float>(bytes / sizeof(float), false);
+      partial_buf_bytes = bytes;
     }
+    for (TcGemm* g : all) g->partials = partial_buf;
   }
+  plan.clear();
+  plan_cond.clear();
   build_plan(plan, false);
   build_plan(plan_cond, true);
+}
+
+void LmImpl::move_to_partition(cudaStream_t st, int sm_budget) {
+  DSM_CUDA(cudaSetDevice(device));
   DSM_CUDA(cudaStreamSynchronize(stream));
+  retired_streams.push_back(stream);     // callers may still hold the old handle (dsm_lm_stream): it stays valid
+  stream = st;
+  graph.reset();                         // captured launches carry the old grids
+  graph_cond.reset();
+  if (sm_budget != sms) tune_plans(sm_budget);
 }
 
 LmImpl::~LmImpl() {
@@ -198,6 +219,7 @@ LmImpl::~LmImpl() {
     cudaEventDestroy(e.second);
   }
   if (stream) cudaStreamDestroy(stream);
+  for (cudaStream_t s : retired_streams) cudaStreamDestroy(s);
 }
 
 static PartialSums partial_sums(const TcGemm& g, bool use_tc) {
@@ -388,6 +410,18 @@ AsrImpl::AsrImpl(MimiImpl* mi, LmImpl* l, int dly, float temperature) : mimi(mi)
   h_prs = static_cast<float*>(arena.alloc_pinned((size_t)std::max(nh, 1) * B * 4));
   h_mask.assign(B, 1);
   items.resize(B);
+  // SM partitions for the two branches of the frame graph (runtime.cuh): the handles move onto the partitions' streams
+  // and re-tune their GEMM grids for the SMs they now own.
+  if (mimi && mimi->spec.with_encoder) {
+    const int want = sm_split_choice(B, lm->kv_dtype != DSM_KV_BF16);
+    if (want > 0) {
+      cudaStream_t s_lm = nullptr, s_codec = nullptr;
+      const SmPartitionInfo part = create_partition_streams(lm->device, want, &s_lm, &s_codec);
+      lm->move_to_partition(s_lm, part.lm_sms);
+      mimi->move_to_partition(s_codec, part.codec_sms);
+      sm_split_lm = part.lm_sms, sm_split_codec = part.codec_sms;
+    }
+  }
   for (cudaEvent_t* e : {&ev_fork, &ev_join}) DSM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   for (cudaEvent_t* e : {&ev_t0, &ev_t1, &ev_m0, &ev_m1, &ev_l0, &ev_l1}) DSM_CUDA(cudaEventCreate(e));
   reset();

@@ -79,9 +79,16 @@ struct LmImpl {
                float* logits_out, float* ys_out);
   void reset_state();
   void reset_batch_idx(int b);
+  // An ASR state that partitions the SMs between its branches (runtime.cuh) hands the LM its stream and budget.
+  void move_to_partition(cudaStream_t st, int sm_budget);
+  int sms = 148;                       // SMs the plans are tuned for
 
  private:
   void build_plan(Plan& p, bool with_cond);
+  void tune_plans(int sm_budget);
+  float* partial_buf = nullptr;
+  size_t partial_buf_bytes = 0;
+  std::vector<cudaStream_t> retired_streams;
 };
 
 struct ItemState {   // asr.rs:16-51
@@ -118,6 +125,7 @@ struct AsrImpl {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_m0 = nullptr, ev_m1 = nullptr,
               ev_l0 = nullptr, ev_l1 = nullptr;
   GraphExec graph_pcm, graph_tokens;
+  int sm_split_lm = 0, sm_split_codec = 0;   // SMs of the two branch partitions (0 = the branches share all SMs)
   float last_ms[3] = {-1.f, -1.f, -1.f};
 
   AsrImpl(MimiImpl* mimi, LmImpl* lm, int delay, float temperature);

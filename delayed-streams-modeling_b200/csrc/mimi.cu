@@ -46,6 +46,8 @@ bool codec_presplit_enabled() {
   return on;
 }
 
+static thread_local CodecGemmRegistry* g_registry = nullptr;
+
 std::shared_ptr<CodecGemm> make_codec_gemm(Arena& arena, const GemmParams& g_in, const std::vector<float>& w_host,
                                            const Tc6Workspace& wsp) {
   auto c = std::make_shared<CodecGemm>();
@@ -58,11 +60,21 @@ std::shared_ptr<CodecGemm> make_codec_gemm(Arena& arena, const GemmParams& g_in,
   // (Tried: the K <= 64 layers -- pure epilogue on the tensor-core kernel -- on the CUDA-core GEMM: slower at every
   // batch size, codec step 2.82 / 2.91 vs 2.79 ms at 256 streams, 14.1 / 15.1 vs 13.9 ms at 2,000.)
   if (c->use_tc) {
-    tc6_prepare(c->t, g, tc6_split_weights(arena, w_host, g.N, g.K), wsp);
+    c->w_planes = tc6_split_weights(arena, w_host, g.N, g.K);
+    c->wsp = wsp;
+    tc6_prepare(c->t, g, c->w_planes, wsp);
   } else {
     c->g.W = arena.upload(w_host);
   }
+  if (g_registry) g_registry->all.push_back(c);
   return c;
+}
+
+void codec_gemm_set_registry(CodecGemmRegistry* r) { g_registry = r; }
+
+void codec_gemms_retune(CodecGemmRegistry& r, int sms) {
+  for (auto& c : r.all)
+    if (c->use_tc) tc6_prepare(c->t, c->g, c->w_planes, c->wsp, sms);
 }
 
 void run_codec_gemm(const CodecGemm& c, cudaStream_t st) {
@@ -440,7 +452,7 @@ MimiImpl::MimiImpl(const dsm_mimi_spec& sp, const dsm_weights* w, int dev, int b
             "mimi spec outside the v0_1 family (n_q=%d qdim=%d dim=%d)", sp.n_q, sp.qdim, sp.dim);
   DSM_CHECK(sp.with_encoder || sp.with_decoder, DSM_ERR_INVALID_ARG, "mimi spec enables neither encoder nor decoder");
   DSM_CUDA(cudaSetDevice(device));
-  stream = create_branch_stream(SmBranch::CODEC, device);
+  DSM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   WeightTable wt(w);
   const bool random = (w == nullptr);
   // Tensor getter: from the table (either of `a|b` alternative names), or seeded host-side random init
@@ -494,6 +506,10 @@ MimiImpl::MimiImpl(const dsm_mimi_spec& sp, const dsm_weights* w, int dev, int b
     emb_all = arena.upload(emb);
     c2_all = arena.upload(c2);
   }
+  struct RegistryScope {
+    explicit RegistryScope(CodecGemmRegistry* r) { codec_gemm_set_registry(r); }
+    ~RegistryScope() { codec_gemm_set_registry(nullptr); }
+  } scope(&gemms);
   if (spec.with_encoder) build_encoder(get, wt);
   if (spec.with_decoder) build_decoder(get, wt);
   reset_state();
@@ -506,6 +522,17 @@ MimiImpl::~MimiImpl() {
   enc_graph.reset();
   dec_graph.reset();
   if (stream) cudaStreamDestroy(stream);
+  for (cudaStream_t s : retired_streams) cudaStreamDestroy(s);
+}
+
+void MimiImpl::move_to_partition(cudaStream_t st, int sm_budget) {
+  DSM_CUDA(cudaSetDevice(device));
+  DSM_CUDA(cudaStreamSynchronize(stream));
+  retired_streams.push_back(stream);     // callers may still hold the old handle (dsm_mimi_stream): it stays valid
+  stream = st;
+  enc_graph.reset();                     // captured launches carry the old grids
+  dec_graph.reset();
+  if (sm_budget != sms) codec_gemms_retune(gemms, sm_budget), sms = sm_budget;
 }
 
 void MimiImpl::build_encoder(const GetFn& get, const WeightTable& wt) {

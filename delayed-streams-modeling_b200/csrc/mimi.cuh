@@ -18,7 +18,15 @@ struct CodecGemm {
   GemmParams g;      // g.W = f32 weights [N, K] on the device
   Tc6Gemm t;
   bool use_tc = false;
+  const __nv_bfloat16* w_planes = nullptr;   // kept so that the GEMM can be re-tuned for another SM budget
+  Tc6Workspace wsp;
 };
+// Every codec GEMM built while a registry is installed (MimiImpl's constructor) is recorded in it.
+struct CodecGemmRegistry {
+  std::vector<std::shared_ptr<CodecGemm>> all;
+};
+void codec_gemm_set_registry(CodecGemmRegistry* r);
+void codec_gemms_retune(CodecGemmRegistry& r, int sms);
 bool codec_gemm_tc_enabled();
 bool codec_presplit_enabled();
 std::shared_ptr<CodecGemm> make_codec_gemm(Arena& arena, const GemmParams& g, const std::vector<float>& w_host,
@@ -72,6 +80,11 @@ struct MimiImpl {
   int* d_first_step = nullptr;     // 1 until the first encode step ran (left_pad_applied, conv.rs:232)
   int* d_first_step_dec = nullptr;
   Tc6Workspace wsp;                // split-K scratch shared by the handle's codec GEMMs
+  CodecGemmRegistry gemms;         // every codec GEMM of both plans (re-tuned when the handle moves to an SM partition)
+  std::vector<cudaStream_t> retired_streams;
+  int sms = 148;                   // SMs the plans are tuned for
+  // An ASR state that partitions the SMs between its branches (runtime.cuh) hands the codec its stream and budget.
+  void move_to_partition(cudaStream_t st, int sm_budget);
 
   // ---- encoder ----
   float* d_pcm = nullptr;          // [B, 1920]

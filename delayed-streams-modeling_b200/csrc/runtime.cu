@@ -6,9 +6,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
-#include <cstring>
 #include <map>
 #include <mutex>
+#include <utility>
 
 namespace dsm {
 
@@ -247,24 +247,17 @@ F driver_fn(const char* name) {
   void* p = nullptr;
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
-    fail(DSM_ERR_UNSUPPORTED, "driver entry point %s is not available (DSM_SM_SPLIT needs CUDA green contexts)", name);
+    fail(DSM_ERR_UNSUPPORTED, "driver entry point %s is not available (SM partitions need CUDA green contexts)", name);
   return reinterpret_cast<F>(p);
 }
-int sm_split_request() {
-  static const int n = [] { const char* e = getenv("DSM_SM_SPLIT"); return e ? atoi(e) : 0; }();
-  return n;
+void cu_check(CUresult r, const char* what) {
+  if (r != CUDA_SUCCESS) fail(DSM_ERR_CUDA, "%s failed with CUresult %d", what, (int)r);
 }
-// "104s": soft split -- the LM branch is confined to its partition, the codec branch may use every SM (it keeps the
-// rest to itself and borrows the LM's SMs whenever the LM's latency-bound GEMMs leave them idle)
-bool sm_split_soft() {
-  static const bool soft = [] { const char* e = getenv("DSM_SM_SPLIT"); return e && strchr(e, 's') != nullptr; }();
-  return soft;
-}
-SmPartition& sm_partition(int device) {
+SmPartition& sm_partition(int device, int lm_sms) {
   static std::mutex mu;
-  static std::map<int, SmPartition> parts;
+  static std::map<std::pair<int, int>, SmPartition> parts;
   std::lock_guard<std::mutex> l(mu);
-  SmPartition& P = parts[device];
+  SmPartition& P = parts[{device, lm_sms}];
   if (P.ok) return P;
   DSM_CUDA(cudaSetDevice(device));
   DSM_CUDA(cudaFree(nullptr));                 // the primary context must exist
@@ -274,49 +267,49 @@ SmPartition& sm_partition(int device) {
       "cuDevSmResourceSplitByCount");
   auto gen = driver_fn<CUresult (*)(CUdevResourceDesc*, CUdevResource*, unsigned int)>("cuDevResourceGenerateDesc");
   auto create = driver_fn<CUresult (*)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int)>("cuGreenCtxCreate");
-  auto chk = [](CUresult r, const char* what) {
-    if (r != CUDA_SUCCESS) fail(DSM_ERR_CUDA, "%s failed with CUresult %d", what, (int)r);
-  };
   CUdevice dev;
-  chk(dev_get(&dev, device), "cuDeviceGet");
+  cu_check(dev_get(&dev, device), "cuDeviceGet");
   CUdevResource all, part[1], rest;
-  chk(get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM), "cuDeviceGetDevResource");
+  cu_check(get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM), "cuDeviceGetDevResource");
   unsigned int groups = 1;
-  chk(split(part, &groups, &all, &rest, 0, (unsigned)sm_split_request()), "cuDevSmResourceSplitByCount");
-  DSM_CHECK(groups == 1 && rest.sm.smCount > 0, DSM_ERR_INVALID_ARG, "DSM_SM_SPLIT=%d leaves no SMs for the codec branch (%u in all)",
-            sm_split_request(), all.sm.smCount);
+  cu_check(split(part, &groups, &all, &rest, 0, (unsigned)lm_sms), "cuDevSmResourceSplitByCount");
+  DSM_CHECK(groups == 1 && rest.sm.smCount > 0, DSM_ERR_INVALID_ARG, "an LM partition of %d SMs leaves none for the codec branch (%u in all)",
+            lm_sms, all.sm.smCount);
   CUdevResource* src[2] = {&part[0], &rest};
   for (int i = 0; i < 2; ++i) {
     CUdevResourceDesc desc;
-    chk(gen(&desc, src[i], 1), "cuDevResourceGenerateDesc");
-    chk(create(&P.ctx[i], desc, dev, CU_GREEN_CTX_DEFAULT_STREAM), "cuGreenCtxCreate");
+    cu_check(gen(&desc, src[i], 1), "cuDevResourceGenerateDesc");
+    cu_check(create(&P.ctx[i], desc, dev, CU_GREEN_CTX_DEFAULT_STREAM), "cuGreenCtxCreate");
     P.sms[i] = (int)src[i]->sm.smCount;
   }
-  fprintf(stderr, "dsm: device %d split into %d SMs (LM branch) + %d SMs (codec branch)\n", device, P.sms[0], P.sms[1]);
   P.ok = true;
   return P;
 }
 }  // namespace
 
-bool sm_split_enabled() { return sm_split_request() > 0; }
-
-int sm_budget(SmBranch which, int device) {
-  if (!sm_split_enabled() || (which == SmBranch::CODEC && sm_split_soft())) return 148;
-  return sm_partition(device).sms[which == SmBranch::LM ? 0 : 1];
+int sm_split_choice(int batch, bool kv_8bit) {
+  static const int forced = [] { const char* e = getenv("DSM_SM_SPLIT"); return e ? atoi(e) : -1; }();
+  if (forced >= 0) return forced;
+  // Measured (tools/gpu_run_ab.sh, gpu_run_ac.sh): with the bf16 ring 96 + 52 SMs wins 9-14 % at
+  // 64, 128, 256, 512, 768 and 1,024 streams; with the int8 ring (half the attention time) 2 % at 256, nothing at
+  // 1,024, and it loses 5-8 % at 2,000, where the LM's projections are tensor-bound and want every SM.  Outside the
+  // measured range the branches share the device.
+  const int hi = kv_8bit ? 512 : 1024;
+  return (batch >= 64 && batch <= hi) ? 96 : 0;
 }
 
-cudaStream_t create_branch_stream(SmBranch which, int device) {
-  cudaStream_t st = nullptr;
-  if (!sm_split_enabled() || (which == SmBranch::CODEC && sm_split_soft())) {
-    DSM_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    return st;
-  }
-  SmPartition& P = sm_partition(device);
+SmPartitionInfo create_partition_streams(int device, int lm_sms, cudaStream_t* lm_stream, cudaStream_t* codec_stream) {
+  SmPartition& P = sm_partition(device, lm_sms);
   auto mk = driver_fn<CUresult (*)(CUstream*, CUgreenCtx, unsigned int, int)>("cuGreenCtxStreamCreate");
-  CUstream cs = nullptr;
-  const CUresult r = mk(&cs, P.ctx[which == SmBranch::LM ? 0 : 1], CU_STREAM_NON_BLOCKING, 0);
-  if (r != CUDA_SUCCESS) fail(DSM_ERR_CUDA, "cuGreenCtxStreamCreate failed with CUresult %d", (int)r);
-  return reinterpret_cast<cudaStream_t>(cs);
+  cudaStream_t* out[2] = {lm_stream, codec_stream};
+  for (int i = 0; i < 2; ++i) {
+    CUstream cs = nullptr;
+    cu_check(mk(&cs, P.ctx[i], CU_STREAM_NON_BLOCKING, 0), "cuGreenCtxStreamCreate");
+    *out[i] = reinterpret_cast<cudaStream_t>(cs);
+  }
+  SmPartitionInfo info;
+  info.lm_sms = P.sms[0], info.codec_sms = P.sms[1];
+  return info;
 }
 
 bool graphs_enabled() {

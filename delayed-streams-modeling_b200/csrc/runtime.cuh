@@ -86,14 +86,19 @@ class GraphExec {
   long long launches_ = 0;  // kernel launches inside one replay
 };
 
-// SM partitioning (CUDA green contexts), opt-in: DSM_SM_SPLIT=<n> gives the LM branch of the frame graph n SMs
-// (rounded to the hardware's granularity) and the codec branch the rest, so that the HBM-bound attention and the
-// tensor / FMA-bound codec kernels run side by side instead of queueing for whole SMs.  The branch streams are then
-// created on the partitions and the persistent GEMM grids are sized to them.
-enum class SmBranch { LM, CODEC };
-bool sm_split_enabled();
-int sm_budget(SmBranch which, int device);                       // SMs of the branch's partition (all of them when off)
-cudaStream_t create_branch_stream(SmBranch which, int device);   // a non-blocking stream on the branch's partition
+// SM partitioning of the frame graph's two branches (CUDA green contexts).  The LM branch is HBM-bound (ring
+// attention at the copy peak) and the codec branch SM-bound (tensor / FMA work); sharing the SMs they queue for whole
+// SMs and the step costs nearly the sum of both.  Confined to disjoint SM sets they overlap: 256 streams 7.45 -> 6.5 ms,
+// 512 streams 14.05 -> 12.1 ms, stt-2.6b x 128 7.54 -> 7.09 ms with 96 + 52 SMs (measured); at
+// 2,000 streams, where the LM's projections are tensor-bound themselves, it loses (37.2 -> 39.0+ ms).
+//   sm_split_choice(B, kv_8bit): SMs for the LM branch of an ASR state with B streams, 0 = no partition.
+//   DSM_SM_SPLIT=<n> forces n (0 = never); unset, the measured rule applies.
+int sm_split_choice(int batch, bool kv_8bit);
+struct SmPartitionInfo {
+  int lm_sms = 0, codec_sms = 0;
+};
+// Creates (once per device and size) the two green contexts and returns a non-blocking stream on each.
+SmPartitionInfo create_partition_streams(int device, int lm_sms, cudaStream_t* lm_stream, cudaStream_t* codec_stream);
 bool graphs_enabled();  // false when DSM_NO_GRAPH=1 or dsm_set_graphs(0)
 void set_graphs_enabled(int v);
 const std::string& last_error();
