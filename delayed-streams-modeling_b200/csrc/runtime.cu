@@ -290,12 +290,12 @@ SmPartition& sm_partition(int device, int lm_sms) {
 int sm_split_choice(int batch, bool kv_8bit) {
   static const int forced = [] { const char* e = getenv("DSM_SM_SPLIT"); return e ? atoi(e) : -1; }();
   if (forced >= 0) return forced;
-  // Measured (tools/gpu_run_ab.sh, gpu_run_ac.sh): with the bf16 ring 96 + 52 SMs wins 9-14 % at
-  // 64, 128, 256, 512, 768 and 1,024 streams; with the int8 ring (half the attention time) 2 % at 256, nothing at
-  // 1,024, and it loses 5-8 % at 2,000, where the LM's projections are tensor-bound and want every SM.  Outside the
-  // measured range the branches share the device.
-  const int hi = kv_8bit ? 512 : 1024;
-  return (batch >= 64 && batch <= hi) ? 96 : 0;
+  // Measured (tools/gpu_run_ab.sh, _ac, _ad): with the bf16 ring 96 + 52 SMs wins 9-14 % at every
+  // batch tried from 8 to 1,536 streams (the memory ceiling is ~1,700); with the int8 ring (half the attention time) it
+  // wins 2-4 % at 256 and 512, nothing at 1,024, and loses 5-8 % at 2,000, where the LM's projections are tensor-bound
+  // and want every SM.  Outside the measured range the branches share the device.
+  if (batch < 8) return 0;
+  return (!kv_8bit || batch <= 1024) ? 96 : 0;
 }
 
 SmPartitionInfo create_partition_streams(int device, int lm_sms, cudaStream_t* lm_stream, cudaStream_t* codec_stream) {
