@@ -416,10 +416,22 @@ AsrImpl::AsrImpl(MimiImpl* mi, LmImpl* l, int dly, float temperature) : mimi(mi)
     const int want = sm_split_choice(B, lm->kv_dtype != DSM_KV_BF16);
     if (want > 0) {
       cudaStream_t s_lm = nullptr, s_codec = nullptr;
-      const SmPartitionInfo part = create_partition_streams(lm->device, want, &s_lm, &s_codec);
-      lm->move_to_partition(s_lm, part.lm_sms);
-      mimi->move_to_partition(s_codec, part.codec_sms);
-      sm_split_lm = part.lm_sms, sm_split_codec = part.codec_sms;
+      SmPartitionInfo part;
+      bool ok = true;
+      try {
+        part = create_partition_streams(lm->device, want, &s_lm, &s_codec);
+      } catch (const Error& e) {
+        // an optimisation, not a requirement (a driver without green contexts, a MIG slice): say so once and share the
+        // SMs -- unless the size was asked for explicitly
+        if (getenv("DSM_SM_SPLIT")) throw;
+        fprintf(stderr, "dsm: SM partition unavailable (%s); the LM and codec branches share the device\n", e.what());
+        ok = false;
+      }
+      if (ok) {
+        lm->move_to_partition(s_lm, part.lm_sms);
+        mimi->move_to_partition(s_codec, part.codec_sms);
+        sm_split_lm = part.lm_sms, sm_split_codec = part.codec_sms;
+      }
     }
   }
   for (cudaEvent_t* e : {&ev_fork, &ev_join}) DSM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));

@@ -295,6 +295,14 @@ int sm_split_choice(int batch, bool kv_8bit) {
   // wins 2-4 % at 256 and 512, nothing at 1,024, and loses 5-8 % at 2,000, where the LM's projections are tensor-bound
   // and want every SM.  Outside the measured range the branches share the device.
   if (batch < 8) return 0;
+  // Nsight Compute / compute-sanitizer cannot instrument kernels launched into green contexts ("Failed to prepare
+  // kernel for profiling"): under an injected tool the branches share the device, so per-kernel captures keep working.
+  static const bool tool = [] {
+    const bool t = getenv("CUDA_INJECTION64_PATH") || getenv("NV_NSIGHT_INJECTION_PORT_BASE") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR");
+    if (t) fprintf(stderr, "dsm: profiling / sanitizer tool attached: SM partition off (set DSM_SM_SPLIT=<n> to force it)\n");
+    return t;
+  }();
+  if (tool) return 0;
   return (!kv_8bit || batch <= 1024) ? 96 : 0;
 }
 

@@ -89,3 +89,26 @@ def test_batch_size_mismatch_is_an_error():
     with pytest.raises(DsmError) as e:       # asr.rs:158-160 "batch size mismatch"
         api.AsrState(gm, gl)
     assert e.value.code == -2
+
+
+def test_sm_partition_follows_the_measured_rule():
+    """An ASR state of >= 8 streams moves its branches onto disjoint SM partitions (runtime.cu: sm_split_choice) and
+    says so; smaller states share the device.  (DSM_SM_SPLIT overrides the rule: then only consistency is checked.)"""
+    import os
+    for B in (2, 8):
+        ga, oa, _keep = _build(B, tiny_lm())
+        lm_sms, codec_sms = ga.sm_partition()
+        forced = os.environ.get("DSM_SM_SPLIT")
+        if forced is None:
+            assert (lm_sms, codec_sms) == ((96, 52) if B >= 8 else (0, 0))
+        elif int(forced) == 0:
+            assert (lm_sms, codec_sms) == (0, 0)
+        else:
+            assert lm_sms >= int(forced) and codec_sms > 0 and lm_sms + codec_sms <= 148
+        audio = synth_audio(B, 4)
+        for i in range(4):
+            pcm = frame(audio, i)
+            om = oa.step_pcm(torch.from_numpy(pcm).unsqueeze(1), None)
+            gm = ga.step_pcm(pcm, None)
+            assert (ga.last_tokens == oa.last_tokens.numpy()).all()
+            assert _strip(gm) == _strip(om)
