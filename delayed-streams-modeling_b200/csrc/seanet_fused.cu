@@ -47,11 +47,14 @@ struct Stage1Params {
 // PCM window and the init conv's weights.  The raw a0 the skip connection adds back is recomputed from PCM in the
 // epilogue (7 FMAs per element, the same order as the first pass, so the same bits) instead of costing a second tile.
 //
-// Thread mapping: shared-memory wavefronts, not FMAs, were the limit of the first version (ncu: 43 % FMA pipe, 2,900
-// wavefronts per warp and tile): a 128-bit LDS is served a quarter-warp at a time, so a load whose lanes mostly
-// repeat each other's addresses still costs four wavefronts.  Here every warp owns one group of output channels --
-// its weight loads are warp-uniform (one wavefront) -- and its lanes own distinct time steps, so activation loads
-// carry 512 distinct bytes per instruction.
+// Thread mapping, third version.  ncu on the second one (each thread a small patch of time steps x channels): FMA pipe
+// 43 % busy, issue slots 57 %, 2,900 shared-memory wavefronts per warp and tile with 28 % bank conflicts -- a 128-bit
+// LDS is served a quarter-warp at a time, so operand loads whose lanes mostly repeat each other's addresses still
+// cost four wavefronts.  Here every warp owns one group of output channels (its weight loads are warp-uniform) and
+// its lanes own distinct time steps (activation loads carry 512 distinct bytes per instruction).  Measured: conflicts
+// 12.6 M -> 3.0 M, wavefronts 2,900 -> 2,400 per warp-tile (a warp-uniform 128-bit load still costs 2-3, not 1), kernel
+// time unchanged (350 vs 339 us): at 12 warps per SM the issue slots, not the LSU, are what is left
+// (profiles/r02w_*, r02x_*).
 __global__ void __launch_bounds__(F1_THREADS, 3) seanet_stage1_kernel(const Stage1Params p) {
   extern __shared__ __align__(16) float f1_smem[];
   float* sw1t = f1_smem;                          // [192][32]

@@ -1,0 +1,10 @@
+#!/bin/bash
+# GPU call AJ (4 GPUs): torchrun N=4 bench line of the final build.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/aj_bench_n4.json 2> gpurun_out/aj_bench_n4.err
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/aj_bench_n4.json").read().strip().splitlines()[-1])
+print(d["n_gpus"], round(d["value"]), round(d["ms_per_step"], 3), round(d["e2e"]["value"]), d["latency"]["p99_ms"], d["clocks"], d["config"].get("sm_partition", {}).get("lm_sms"))
+PY
