@@ -290,11 +290,10 @@ SmPartition& sm_partition(int device, int lm_sms) {
 int sm_split_choice(int batch, bool kv_8bit) {
   static const int forced = [] { const char* e = getenv("DSM_SM_SPLIT"); return e ? atoi(e) : -1; }();
   if (forced >= 0) return forced;
-  // Measured (tools/gpu_run_ab.sh, _ac, _ad): with the bf16 ring 96 + 52 SMs wins 9-14 % at every
-  // batch tried from 8 to 1,536 streams (the memory ceiling is ~1,700); with the int8 ring (half the attention time) it
+  // Measured (tools/gpu_run_ab.sh, _ac, _ad, _ao): with the bf16 ring 96 + 52 SMs wins 5-14 % at every
+  // batch tried from 1 to 1,536 streams (the memory ceiling is ~1,700); with the int8 ring (half the attention time) it
   // wins 2-4 % at 256 and 512, nothing at 1,024, and loses 5-8 % at 2,000, where the LM's projections are tensor-bound
   // and want every SM.  Outside the measured range the branches share the device.
-  if (batch < 8) return 0;
   // Nsight Compute / compute-sanitizer cannot instrument kernels launched into green contexts ("Failed to prepare
   // kernel for profiling"): under an injected tool the branches share the device, so per-kernel captures keep working.
   static const bool tool = [] {

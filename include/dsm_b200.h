@@ -255,7 +255,8 @@ dsm_status dsm_asr_last_logits(dsm_asr* h, float* logits);
 dsm_status dsm_asr_last_step_ms(dsm_asr* h, float out[3]);
 /* SM partition of the state's two branches (no reference counterpart: candle runs one stream).  A state built from
  * a Mimi encoder and an LM confines the LM branch (HBM-bound ring attention) and the codec branch (tensor / FMA-bound)
- * to disjoint SM sets -- CUDA green contexts -- when that was measured to pay (128..512 streams; DSM_SM_SPLIT=<LM SMs>
+ * to disjoint SM sets -- CUDA green contexts -- when that was measured to pay (bf16 ring: always; 8-bit rings: up to
+ * 1,024 streams; DSM_SM_SPLIT=<LM SMs>
  * forces a size, 0 disables).  out[0] = SMs of the LM branch, out[1] = SMs of the codec branch; both 0 when the
  * branches share the device.  The handles passed to dsm_asr_create then run on the partition's streams (dsm_lm_stream
  * / dsm_mimi_stream return the new ones; handles obtained earlier stay valid but idle). */

@@ -92,15 +92,15 @@ def test_batch_size_mismatch_is_an_error():
 
 
 def test_sm_partition_follows_the_measured_rule():
-    """An ASR state of >= 8 streams moves its branches onto disjoint SM partitions (runtime.cu: sm_split_choice) and
-    says so; smaller states share the device.  (DSM_SM_SPLIT overrides the rule: then only consistency is checked.)"""
+    """An ASR state with the bf16 ring moves its branches onto disjoint SM partitions (runtime.cu: sm_split_choice)
+    and says so.  (DSM_SM_SPLIT overrides the rule: then only consistency is checked.)"""
     import os
     for B in (2, 8):
         ga, oa, _keep = _build(B, tiny_lm())
         lm_sms, codec_sms = ga.sm_partition()
         forced = os.environ.get("DSM_SM_SPLIT")
         if forced is None:
-            assert (lm_sms, codec_sms) == ((96, 52) if B >= 8 else (0, 0))
+            assert (lm_sms, codec_sms) == (96, 52)
         elif int(forced) == 0:
             assert (lm_sms, codec_sms) == (0, 0)
         else:

@@ -22,7 +22,7 @@ VARIANTS = [
     ({"DSM_TC_MAXSPLIT": "1"}, ["tests/test_gpu_lm.py"]),
     ({"DSM_CODEC_GEMM": "simt", "DSM_LM_GEMM": "simt"}, ["tests/test_gpu_asr.py"]),
     ({"DSM_NO_GRAPH": "1"}, ["tests/test_gpu_asr.py"]),
-    ({"DSM_SM_SPLIT": "0"}, ["tests/test_gpu_full_size.py", "tests/test_gpu_asr.py"]),   # states of >= 8 streams partition the SMs by default
+    ({"DSM_SM_SPLIT": "0"}, ["tests/test_gpu_full_size.py", "tests/test_gpu_asr.py"]),   # ASR states partition the SMs by default
     ({"DSM_SM_SPLIT": "96"}, ["tests/test_gpu_asr.py"]),               # forced on small batches: re-tuned GEMM grids
     ({"DSM_SM_SPLIT": "64"}, ["tests/test_gpu_full_size.py"]),
 ]
