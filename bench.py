@@ -24,6 +24,9 @@ Beyond the base contract the line carries: `roofline.step_frac` (SURVEY 8(d) alg
 step time / HBM peak), `latency` (p50 / p99 of single steps through the public call with host PCM, over
 --latency-steps steps: the metric's "real-time" clause is p99 <= 80 ms), `realtime_streams_live` (the batch, if it
 meets that clause) and, with --live-sweep, `live_streams_max` (largest swept batch that fits and meets it).
+`config.sm_partition` says whether the ASR state put its LM and codec branches on disjoint SM sets (CUDA green contexts,
+DESIGN.md section 6; DSM_SM_SPLIT=0 in the environment turns that off) -- `roofline.frac` and `lm_step_ms` are then
+measured inside the LM branch's partition.
 """
 from __future__ import annotations
 
